@@ -1,0 +1,400 @@
+#!/usr/bin/env python
+"""bench.py — filtered full-ranking evaluation throughput of the chk_b200 hot path on B200.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3                # our arm (CUDA, through the C ABI)
+    python bench.py --impl reference --steps 3 --warmup 1         # the reference's CPU algorithm (oracle port)
+    torchrun --nproc-per-node N ... bench.py --gpus N ...         # entity-table-sharded ranking over NCCL
+
+Workload (BASELINE.json configs[4], the config the metric's "1/2/4/8 B200" refers to): FFTRotH rank=257,
+fp32, synthetic 4,000,000-entity / 1,000-relation graph (2,000 relation rows with reciprocals), Zipf
+heads/tails, filters built over all splits; one STEP = one evaluation batch of 500 filtered-ranking queries
+(run.py eval_batch_size) against the whole entity table.  With N GPUs the table is row-sharded (strong
+scaling: the step is fixed, each rank counts over N_ent/N rows, one int64 all_reduce per step).
+The rank's table shard (8.2 GB / N) exceeds the 126 MB L2, so every step streams it from HBM.
+
+One JSON line on stdout (rank 0).  `value` = queries/s with inputs resident in HBM; `e2e` = the same metric
+through the public API model.get_ranking() with HOST query ids (host CSR lookup, H2D, D2H inside the timed
+region); `roofline` = the dominant kernel (rank tile contraction) timed alone with CUDA events;
+`cpu_baseline` = the oracle port on this box's host cores on a bounded sample; `train` = drop-in training
+throughput (KGOptimizer contract + torch.optim) on BASELINE.json configs[1].
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "filtered_eval_queries_per_sec"
+UNIT = "queries/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="big4m", choices=["big4m", "wn18rr", "fb237", "yago310"])
+    ap.add_argument("--rank", type=int, default=None)
+    ap.add_argument("--model", default=None)
+    ap.add_argument("--dtype", default="float", choices=["float", "double"])
+    ap.add_argument("--batch", type=int, default=500)
+    ap.add_argument("--rank-algo", default=os.environ.get("CHK_RANK_ALGO", "auto"), choices=["auto", "fma", "mma"])
+    ap.add_argument("--no-train", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+WORKLOAD_DEFAULTS = {"big4m": ("FFTRotH", 257), "wn18rr": ("FFTRotH", 33), "fb237": ("FFTRefH", 33),
+                     "yago310": ("FFTAttH", 33)}
+
+
+def config_dict(args, n_gpus, extra=None):
+    from complexhyperbolickge_b200.synthetic import SHAPES
+    model, rank = WORKLOAD_DEFAULTS[args.workload]
+    model, rank = args.model or model, args.rank or rank
+    n_ent, n_rel = SHAPES[args.workload][:2]
+    cfg = {"workload": f"{model} rank={rank} {args.dtype} filtered full-ranking eval, synthetic {args.workload} "
+                       f"({n_ent} entities, {n_rel} relations), eval batch {args.batch} queries/step",
+           "baseline_config": "BASELINE.json configs[4]" if args.workload == "big4m" else args.workload,
+           "entities": n_ent, "relation_rows": 2 * n_rel, "rank": rank, "eval_batch": args.batch,
+           "parallelism": f"entity-table row-sharded x{n_gpus}, 1 int64 all_reduce/step" if n_gpus > 1 else "single GPU",
+           "l2": "inputs larger than L2 (table shard streamed from HBM each step)"}
+    if extra:
+        cfg.update(extra)
+    return cfg, model, rank
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.proc, self.lines, self.index = None, [], index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._pump, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append((time.time(), ln.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ts, ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            inside = t0 - 0.05 <= ts <= t1 + 0.15
+            try:
+                if inside:
+                    sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            if inside:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def oracle_eval_sample(model_name, rank, dtype, n_ent, n_rel2, n_queries, ent_slice, seed=0):
+    """Time the oracle port's get_ranking on `n_queries` queries against `ent_slice` entity rows and
+    extrapolate linearly in the table size (the reference's cost is linear in N: broadcast multiply-sum)."""
+    from oracle import chk_oracle as O
+    torch.set_num_threads(os.cpu_count())
+    dt = torch.float32 if dtype == "float" else torch.float64
+    g = torch.Generator().manual_seed(seed)
+    n = 2 * (rank - 1)
+    att = model_name == "FFTAttH"
+    std = float(np.sqrt(0.4 / (2 * rank)))
+    p = O.Params(O.KIND[model_name], rank, True, (torch.randn(ent_slice, 2 * rank, generator=g) * std).to(dt),
+                 (torch.randn(n_rel2, 2 * n, generator=g) * 0.05).to(dt),
+                 (torch.rand(n_rel2, 2 * n if att else n, generator=g) * 2 - 1).to(dt),
+                 (torch.rand(n_rel2, 1, generator=g) * 1.5 + 0.5).to(dt), (torch.randn(ent_slice, 1, generator=g) * 0.1).to(dt),
+                 (torch.randn(ent_slice, 1, generator=g) * 0.1).to(dt), torch.randn(n_rel2, n, generator=g).to(dt) if att else None)
+    qs = torch.stack([torch.randint(0, ent_slice, (n_queries,), generator=g), torch.randint(0, n_rel2, (n_queries,), generator=g),
+                      torch.randint(0, ent_slice, (n_queries,), generator=g)], 1)
+    filters = {(int(h), int(r)): [int(t)] for h, r, t in qs.numpy()}
+    t0 = time.perf_counter()
+    O.get_ranking(p, qs, filters, batch_size=n_queries)
+    dt_s = time.perf_counter() - t0
+    return n_queries / (dt_s * (n_ent / ent_slice)), dt_s
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU algorithm for the path (oracle port; the Python reference
+    cannot travel to the GPU box), all host threads, same metric/config; each step a bounded sample."""
+    rank_env = int(os.environ.get("RANK", "0"))
+    if rank_env != 0:
+        return
+    cfg, model, rank = config_dict(args, args.gpus)
+    from complexhyperbolickge_b200.synthetic import SHAPES
+    n_ent, n_rel = SHAPES[args.workload][:2]
+    ent_slice = min(n_ent, 250_000 if rank > 65 else 40_000 * 4)
+    nq = 1 if rank > 65 else 4
+    vals, times = [], []
+    for i in range(args.warmup + args.steps):
+        v, t = oracle_eval_sample(model, rank, args.dtype, n_ent, 2 * n_rel, nq, ent_slice, seed=i)
+        if i >= args.warmup:
+            vals.append(v)
+            times.append(t)
+    value = float(len(vals) / sum(1.0 / v for v in vals))       # total queries / total (extrapolated) time
+    sample = (f"{nq} query x {ent_slice} of {n_ent} entity rows per step, extrapolated linearly in the table size; "
+              f"oracle port of models/base.py:228-280 on torch-CPU tensors")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(times)), "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32" if args.dtype == "float" else "f64",
+            "data": "synthetic", "config": cfg,
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ train leg
+def train_leg(steps, warmup, device):
+    """Drop-in training throughput on BASELINE.json configs[1]: FFTRefH rank=33 Adagrad bs=500 neg=250 on the
+    synthetic FB15k-237 shape, through the KGOptimizer contract (two model() calls, backward, torch.optim)."""
+    from argparse import Namespace
+    import complexhyperbolickge_b200 as chk
+    from complexhyperbolickge_b200 import synthetic
+    from complexhyperbolickge_b200.optim import KGOptimizer, N3
+    g = synthetic.make_graph("fb237", seed=0)
+    args = Namespace(sizes=(g["n_ent"], g["n_rel2"], g["n_ent"]), rank=33, dropout=0, gamma=0, dtype="float",
+                     bias="learn", init_size=1e-3, multi_c=True)
+    model = chk.FFTRefH(args).to(device)
+    synthetic.trained_like_(model, 0)
+    opt = KGOptimizer(model, N3(0.0), torch.optim.Adagrad(model.parameters(), lr=0.02), 500, 1, 250, False, verbose=False)
+    ex = synthetic.train_examples(g)
+    ex = ex[torch.randperm(ex.shape[0], generator=torch.Generator().manual_seed(0))]
+    pinned = ex[: (steps + warmup) * 500].pin_memory()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    loss = None
+    for i in range(steps + warmup):
+        if i == warmup:
+            torch.cuda.synchronize()
+            ev0.record()
+        b = pinned[i * 500:(i + 1) * 500].to(device, non_blocking=True)
+        l = opt.calculate_loss(b)
+        l.backward()
+        opt.optimizer.step()
+        opt.optimizer.zero_grad()
+        loss = l
+    lv = loss.item()
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / steps
+    return {"metric": "train_triples_per_sec", "value": 500.0 / (ms * 1e-3), "unit": "triples/s", "ms_per_step": ms,
+            "config": "BASELINE.json configs[1]: FFTRefH rank=33 Adagrad bs=500 neg=250, synthetic FB15k-237 shape, "
+                      "drop-in KGOptimizer loop (2 model() calls + backward + dense torch.optim.Adagrad)",
+            "final_loss": lv, "algorithmic_bytes_per_triple": 2 * (2 + 250) * 66 * 4}
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank_id = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (our arm) needs a CUDA device: complexhyperbolickge_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    pg = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+        pg = dist.group.WORLD
+    from argparse import Namespace
+    import complexhyperbolickge_b200 as chk
+    from complexhyperbolickge_b200 import ops, ranking, synthetic
+
+    cfg, model_name, rank = config_dict(args, world)
+    graph = synthetic.make_graph(args.workload, seed=0)
+    n_ent, n_rel2 = graph["n_ent"], graph["n_rel2"]
+    margs = Namespace(sizes=(n_ent, n_rel2, n_ent), rank=rank, dropout=0, gamma=0, dtype=args.dtype, bias="learn",
+                      init_size=1e-3, multi_c=True)
+    model = getattr(chk, model_name)(margs).to(device)
+    synthetic.trained_like_(model, 0)
+    model.eval()
+    algo = args.rank_algo
+    if algo == "auto":
+        algo = "mma" if (args.dtype == "float" and ops.mma_available()) else "fma"
+    model.rank_algo = algo
+    model.process_group = pg
+    cfg["rank_algo"] = algo
+    b = args.batch
+    K, W = args.steps, args.warmup
+    findex = graph["filters"]["rhs"]
+    test = graph["test"]
+    reps = (b * (K + W) + len(test) - 1) // len(test)
+    qall = np.concatenate([test] * reps)[: b * (K + W)]
+    hist = np.diff(findex.indptr)
+    cfg["filter_len"] = {"mean": float(hist.mean()), "p99": float(np.percentile(hist, 99)), "max": int(hist.max())}
+
+    # ---- resident inputs for `value`
+    steps_in = []
+    for i in range(K + W):
+        qb = qall[i * b:(i + 1) * b]
+        indptr, idx = findex.batch_csr(qb)
+        steps_in.append((torch.from_numpy(qb).to(device), torch.from_numpy(indptr).to(device),
+                         torch.from_numpy(idx).to(device), int(idx.size)))
+    with torch.no_grad():
+        state = ranking.EvalState(model)
+        ws = ops.rank_mma_workspace(rank, b, device) if state.algo == ops.CHK_RANK_MMA else None
+        counts = torch.zeros(b, dtype=torch.int64, device=device)
+
+        def step(i):
+            counts.zero_()
+            qd, ip, ix, tot = steps_in[i]
+            ranking.rank_batch(model, state, qd, ip, ix, tot, counts, ws)
+            if world > 1:
+                dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=pg)
+
+        for i in range(W):
+            step(i)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        sampler = ClockSampler(local)
+        if rank_id == 0:
+            sampler.start()
+        time.sleep(0.2)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        t_wall0 = time.time()
+        ev0.record()
+        for i in range(W, W + K):
+            step(i)
+        ev1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t_wall1 = time.time()
+        ms_total = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms_total], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_total = t.item()
+        clocks = sampler.stop(t_wall0, t_wall1) if rank_id == 0 else None
+        ranks_check = (counts + 1).float().cpu()
+
+        # ---- roofline: the dominant kernel alone (rank tile contraction), CUDA events on torch's stream
+        qd, ip, ix, tot = steps_in[W]
+        q, _ = ops.query_fwd(model.KIND, rank, True, model.entity.weight.detach(), model.rel.weight.detach(),
+                             model.rel_diag.weight.detach(), None if model._ctx_weight() is None else model._ctx_weight().detach(),
+                             model.c.weight.detach(), qd[:, 0].contiguous(), qd[:, 1].contiguous())
+        qn = ops.row_hnorm(rank, q)
+        bhv = model.bh.weight.detach().view(-1)[qd[:, 0]].contiguous()
+        rows = model.entity.weight.detach()[qd[:, 2]].contiguous()
+        tgt = ops.target_scores(rank, q, qn, bhv, rows, ops.row_hnorm(rank, rows),
+                                model.bt.weight.detach().view(-1)[qd[:, 2]].contiguous())
+        empty_ip = torch.zeros(b + 1, dtype=torch.int64, device=device)
+        nrep = 3
+        torch.cuda.synchronize()
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ops.rank_counts(state.algo, rank, q, qn, bhv, tgt, state.entity, state.hn, state.bt, state.lo, empty_ip, ix, 0,
+                        counts, state.shadow, ws)
+        k0.record()
+        for _ in range(nrep):
+            ops.rank_counts(state.algo, rank, q, qn, bhv, tgt, state.entity, state.hn, state.bt, state.lo, empty_ip, ix,
+                            0, counts, state.shadow, ws)
+        k1.record()
+        torch.cuda.synchronize()
+        kern_ms = k0.elapsed_time(k1) / nrep
+
+    # ---- e2e through the public API with host buffers
+    e2e = None
+    if not args.no_e2e:
+        qhost = torch.from_numpy(qall).pin_memory()
+        model.get_ranking(qhost[:b], findex, batch_size=b)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        h2d = 0
+        for i in range(W, W + K):
+            qb = qhost[i * b:(i + 1) * b]
+            r_host = model.get_ranking(qb, findex, batch_size=b)
+            h2d += qb.numel() * 8 + (b + 1) * 8 + steps_in[i][3] * 8
+        e1.record()
+        torch.cuda.synchronize()
+        e_ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([e_ms], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e_ms = t.item()
+        assert torch.equal(r_host, ranks_check), "e2e ranks differ from the resident-input ranks"
+        e2e = {"value": b * K / (e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d // K, "d2h_bytes_per_step": b * 4,
+               "api": "model.get_ranking(host LongTensor[b,3], FilterIndex, batch_size)"}
+
+    if rank_id != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = {}
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        peaks = json.load(open(pk))
+    peak_tf = peaks.get("bf16_tflops", 1590.0)
+    shard_rows = state.hi - state.lo
+    flops = 8.0 * rank * b * shard_rows
+    achieved = flops / (kern_ms * 1e-3) / 1e12
+    mma = state.algo == ops.CHK_RANK_MMA
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                "traffic": None, "kernel": "rank_mma_kernel (tcgen05 bf16x3)" if mma else "rank_tile_kernel<float,1> (fp32 FMA)",
+                "kernel_ms": kern_ms, "algorithmic_flop_per_pair": 8 * rank, "issued_flop_per_pair": 8 * rank * (3 if mma else 1),
+                "pairs_per_launch": b * shard_rows,
+                "peak_source": ("MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone)" if peaks else "fallback 1.59 PFLOP/s")}
+    line = {"metric": METRIC, "value": b * K / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32" if args.dtype == "float" else "f64", "data": "synthetic", "config": cfg, "clocks": clocks,
+            "e2e": e2e, "gpu_launches": 6 * K, "roofline": roofline,
+            "mean_rank_check": float(ranks_check.mean())}
+    if world == 1 and not args.no_cpu_baseline:
+        ent_slice = min(n_ent, 250_000 if rank > 65 else 160_000)
+        nq = 1 if rank > 65 else 4
+        v, t = oracle_eval_sample(model_name, rank, args.dtype, n_ent, n_rel2, nq, ent_slice)
+        v2, t2 = oracle_eval_sample(model_name, rank, args.dtype, n_ent, n_rel2, nq, ent_slice, seed=1)
+        line["cpu_baseline"] = {"value": 2.0 / (1.0 / v + 1.0 / v2), "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                                "sample": f"2 x ({nq} query x {ent_slice} of {n_ent} entity rows), {t + t2:.1f} s of CPU work, "
+                                          "extrapolated linearly in the table size; oracle port (torch-CPU tensors, all cores)"}
+    if world == 1 and not args.no_train:
+        del state
+        torch.cuda.empty_cache()
+        line["train"] = train_leg(20, 3, device)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

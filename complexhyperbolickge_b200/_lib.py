@@ -1,0 +1,70 @@
+"""ctypes binding of libchk_b200.so (the C ABI declared in include/chk_b200.h).
+
+The shared library is built in-tree (``make -C complexhyperbolickge_b200/csrc`` or
+``__graft_entry__.build()``).  There is no CPU fallback and no alternative backend: if the library is
+missing, or a call fails, a RuntimeError is raised.
+"""
+import ctypes
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libchk_b200.so")
+CSRC = os.path.join(_HERE, "csrc")
+
+CHK_ROT, CHK_REF, CHK_ATT = 0, 1, 2
+CHK_F32, CHK_F64 = 0, 1
+CHK_RANK_FMA, CHK_RANK_MMA = 0, 1
+
+_i, _i64, _p = ctypes.c_int, ctypes.c_int64, ctypes.c_void_p
+
+# name -> (restype, argtypes); mirrors include/chk_b200.h line by line
+SIGNATURES = {
+    "chk_abi_version": (_i, []),
+    "chk_last_error": (ctypes.c_char_p, []),
+    "chk_query_fwd": (_i, [_i, _i, _i, _i64, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "chk_query_bwd": (_i, [_i, _i, _i, _i64, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "chk_score_gather_fwd": (_i, [_i, _i, _i64, _i64, _p, _i64, _i64, _p, _p, _i64, _p, _i64, _i64, _p, _p, _p]),
+    "chk_score_gather_bwd": (_i, [_i, _i, _i64, _i64, _p, _i64, _i64, _p, _p, _i64, _p, _p, _p, _p]),
+    "chk_scatter_add_rows": (_i, [_i, _p, _p, _p, _i64, _i64, _p]),
+    "chk_row_hnorm": (_i, [_i, _i, _i64, _p, _p, _p]),
+    "chk_score_all": (_i, [_i, _i, _i64, _p, _p, _p, _p, _p, _p, _i64, _p, _p]),
+    "chk_target_scores": (_i, [_i, _i, _i64, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "chk_rank_counts": (_i, [_i, _i, _i, _i64, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _p, _p, _i64, _p, _p, _i64,
+                             _p, _p]),
+    "chk_entity_shadow_bytes": (_i64, [_i, _i64]),
+    "chk_entity_shadow_build": (_i, [_i, _i64, _p, _p, _p]),
+    "chk_rank_mma_workspace_bytes": (_i64, [_i, _i64]),
+}
+
+_lib = None
+
+
+def build_native(verbose: bool = False) -> str:
+    """Compile every CUDA source for sm_100a into libchk_b200.so (nvcc cross-compiles without a GPU)."""
+    out = subprocess.run(["make", "-C", CSRC, "-j8"], capture_output=True, text=True)
+    if out.returncode != 0:
+        raise RuntimeError("building libchk_b200.so failed:\n" + out.stdout[-4000:] + out.stderr[-4000:])
+    if verbose:
+        print(out.stdout[-2000:])
+    return LIB_PATH
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `make -C {CSRC}` (or __graft_entry__.build()). "
+                "complexhyperbolickge_b200 has no CPU / eager fallback.")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise RuntimeError(f"{what} failed (code {rc}): {lib().chk_last_error().decode()}")

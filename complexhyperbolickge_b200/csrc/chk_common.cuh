@@ -1,0 +1,112 @@
+// Shared device helpers for the chk_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include "../../include/chk_b200.h"
+
+#define CHK_FULL 0xffffffffu
+
+void chk_set_error(const char* fmt, ...);
+
+#define CHK_CUDA_LAUNCH_CHECK(name)                                              \
+    do {                                                                         \
+        cudaError_t e__ = cudaGetLastError();                                    \
+        if (e__ != cudaSuccess) {                                                \
+            chk_set_error("%s: %s", name, cudaGetErrorString(e__));              \
+            return CHK_ECUDA;                                                    \
+        }                                                                        \
+    } while (0)
+
+// ---- scalar traits -------------------------------------------------------------------------
+template <typename T> struct Sc;
+template <> struct Sc<float> {
+    static constexpr float ball_eps = 4e-3f;      // utils/complexhyperbolic.py:13
+    static constexpr float min_norm = 1e-15f;     // :12
+    static constexpr float proj_top = (float)(1.0 - 1e-5);   // python double 1-1e-5 cast to fp32, :83-84
+    __device__ static __forceinline__ float sqrt_(float x) { return sqrtf(x); }
+    __device__ static __forceinline__ float tanh_(float x) { return tanhf(x); }
+    __device__ static __forceinline__ float exp_(float x) { return expf(x); }
+    __device__ static __forceinline__ float log1p_(float x) { return log1pf(x); }
+    __device__ static __forceinline__ float fma_(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+    __device__ static __forceinline__ float max_(float a, float b) { return fmaxf(a, b); }
+    __device__ static __forceinline__ float min_(float a, float b) { return fminf(a, b); }
+    __device__ static __forceinline__ float abs_(float a) { return fabsf(a); }
+};
+template <> struct Sc<double> {
+    static constexpr double ball_eps = 1e-5;
+    static constexpr double min_norm = 1e-15;
+    static constexpr double proj_top = 1.0 - 1e-5;
+    __device__ static __forceinline__ double sqrt_(double x) { return sqrt(x); }
+    __device__ static __forceinline__ double tanh_(double x) { return tanh(x); }
+    __device__ static __forceinline__ double exp_(double x) { return exp(x); }
+    __device__ static __forceinline__ double log1p_(double x) { return log1p(x); }
+    __device__ static __forceinline__ double fma_(double a, double b, double c) { return __fma_rn(a, b, c); }
+    __device__ static __forceinline__ double max_(double a, double b) { return fmax(a, b); }
+    __device__ static __forceinline__ double min_(double a, double b) { return fmin(a, b); }
+    __device__ static __forceinline__ double abs_(double a) { return fabs(a); }
+};
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(CHK_FULL, v, o);
+    return v;
+}
+
+template <typename T>
+__device__ __forceinline__ void warp_sum3(T& a, T& b, T& c) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        T ta = __shfl_xor_sync(CHK_FULL, a, o);
+        T tb = __shfl_xor_sync(CHK_FULL, b, o);
+        T tc = __shfl_xor_sync(CHK_FULL, c, o);
+        a += ta; b += tb; c += tc;
+    }
+}
+
+// ---- the canonical pair score ----------------------------------------------------------------
+// Everything that must agree bit-for-bit between kernels (target score, rank tiles, filter pass,
+// exact re-check of the tensor-core tier) goes through these two functions.
+//
+// Hermitian norm of a row sum, clamped: utils/complexhyperbolic.py:229-230.
+template <typename T>
+__device__ __forceinline__ T clamp_hnorm(T sumsq) {
+    T v = sumsq - T(1);
+    v = Sc<T>::max_(v, T(-1));
+    return Sc<T>::min_(v, -Sc<T>::ball_eps);
+}
+
+// re = Re sum z conj(w) (WITHOUT the -1), im likewise; zn, wn clamped norms.
+// x = 2|zw|^2/zn/wn - 1 clamped at 1+eps (utils/complexhyperbolic.py:231-234), d = acosh(x).
+template <typename T>
+__device__ __forceinline__ T clamped_x(T re, T im, T zn, T wn) {
+    T r1 = re - T(1);
+    T mod2 = Sc<T>::fma_(r1, r1, im * im);
+    T x = (T(2) * mod2) / zn / wn - T(1);
+    return Sc<T>::max_(x, T(1) + Sc<T>::ball_eps);
+}
+
+template <typename T>
+__device__ __forceinline__ T acosh_x(T x) {
+    // acosh(x) = log1p((x-1) + sqrt((x-1)(x+1))): accurate for x -> 1+
+    T xm = x - T(1);
+    return Sc<T>::log1p_(xm + Sc<T>::sqrt_(xm * (x + T(1))));
+}
+
+// score = (bh + bt) + (-d^2)  in that order (models/base.py:171); has_bias==false -> -d^2.
+template <typename T>
+__device__ __forceinline__ T pair_score(T re, T im, T zn, T wn, bool has_bias, T bh, T bt) {
+    T d = acosh_x(clamped_x(re, im, zn, wn));
+    T s = -(d * d);
+    return has_bias ? (bh + bt) + s : s;
+}
+
+// Canonical dot chain over complex index k (zr,zi,wr,wi are the four real planes of the two rows).
+template <typename T>
+__device__ __forceinline__ void dot_step(T zr, T zi, T wr, T wi, T& re, T& im) {
+    re = Sc<T>::fma_(zr, wr, re);
+    re = Sc<T>::fma_(zi, wi, re);
+    im = Sc<T>::fma_(zi, wr, im);
+    im = Sc<T>::fma_(-zr, wi, im);
+}

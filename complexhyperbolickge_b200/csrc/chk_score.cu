@@ -1,0 +1,213 @@
+// K3 — scoring of gathered tails, forward and fused backward (training path), plus the row scatter-add.
+//
+// Replaces, for B queries x nt tails: KGModel.get_rhs gather (reference models/base.py:128-133),
+// FFTUnitBall.similarity_score -> Distance.forward (models/complexhyperbolic.py:45-59,
+// utils/complexhyperbolic.py:212-237, lift=True Hermitian form :176-178), the bias add
+// (models/base.py:171) and Distance.backward/grad (utils/complexhyperbolic.py:192-210,239-254).
+//
+// One CTA per query row b; its warps split the nt tails.  Lane l owns complex coefficients
+// k = l, l+32, ... of both rows, so the 2r-wide tail row is read with coalesced loads exactly once and
+// nothing but the scores (fwd) / gradient rows (bwd) is written.  The backward recomputes the five pair
+// scalars (re, im, zn, wn, x) instead of saving the reference's seven (b, nt, r) tensors.
+#include "chk_common.cuh"
+
+namespace {
+
+constexpr int kWarps = 8;
+
+template <typename T> struct SArgs {
+    const T* q; int64_t q_stride_b, q_stride_j;
+    const T* table; const int64_t* tail_idx; int64_t row_stride_b;
+    const T* bh_vals; int64_t bh_stride_b, bh_stride_j; const T* bt;
+    int64_t B, nt; int r;
+    T* scores;                       // fwd
+    const T* grad_scores; T* grad_q; T* grad_rows;   // bwd
+};
+
+template <typename T, int NITER>
+__device__ __forceinline__ void load_row(const T* __restrict__ row, int r, int lane, T (&re)[NITER], T (&im)[NITER]) {
+#pragma unroll
+    for (int i = 0; i < NITER; ++i) {
+        int k = lane + 32 * i;
+        bool ok = k < r;
+        re[i] = ok ? row[k] : T(0);
+        im[i] = ok ? row[r + k] : T(0);
+    }
+}
+
+template <typename T, int NITER, bool BWD>
+__global__ void __launch_bounds__(kWarps * 32) score_gather_kernel(SArgs<T> A) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int r = A.r;
+    extern __shared__ unsigned char smem_raw[];
+    T* red = reinterpret_cast<T*>(smem_raw);          // [kWarps][2r] for the grad_q reduction (BWD)
+    for (int64_t b = blockIdx.x; b < A.B; b += gridDim.x) {
+        T zr[NITER], zi[NITER], gzr[NITER], gzi[NITER];
+        T zn = T(0);
+        const bool per_pair_q = A.q_stride_j != 0;
+        if (!per_pair_q) {
+            load_row<T, NITER>(A.q + b * A.q_stride_b * 2 * r, r, lane, zr, zi);
+            T s = T(0);
+#pragma unroll
+            for (int i = 0; i < NITER; ++i) { s = Sc<T>::fma_(zr[i], zr[i], s); s = Sc<T>::fma_(zi[i], zi[i], s); }
+            zn = clamp_hnorm<T>(warp_sum<T>(s));
+        }
+#pragma unroll
+        for (int i = 0; i < NITER; ++i) { gzr[i] = T(0); gzi[i] = T(0); }
+        for (int64_t j = warp; j < A.nt; j += kWarps) {
+            const int64_t pair = b * A.nt + j;
+            const int64_t row = A.tail_idx ? A.tail_idx[pair] : (b * A.row_stride_b + j);
+            T wr[NITER], wi[NITER];
+            load_row<T, NITER>(A.table + row * 2 * r, r, lane, wr, wi);
+            if (per_pair_q) {
+                load_row<T, NITER>(A.q + (b * A.q_stride_b + j * A.q_stride_j) * 2 * r, r, lane, zr, zi);
+                T s = T(0);
+#pragma unroll
+                for (int i = 0; i < NITER; ++i) { s = Sc<T>::fma_(zr[i], zr[i], s); s = Sc<T>::fma_(zi[i], zi[i], s); }
+                zn = clamp_hnorm<T>(warp_sum<T>(s));
+            }
+            T re = T(0), im = T(0), ws = T(0);
+#pragma unroll
+            for (int i = 0; i < NITER; ++i) {
+                dot_step<T>(zr[i], zi[i], wr[i], wi[i], re, im);
+                ws = Sc<T>::fma_(wr[i], wr[i], ws); ws = Sc<T>::fma_(wi[i], wi[i], ws);
+            }
+            warp_sum3<T>(re, im, ws);
+            const T wn = clamp_hnorm<T>(ws);
+            const T x = clamped_x<T>(re, im, zn, wn);
+            const T d = acosh_x<T>(x);
+            if (!BWD) {
+                if (lane == 0) {
+                    T s = -(d * d);
+                    A.scores[pair] = A.bt ? (A.bh_vals[b * A.bh_stride_b + j * A.bh_stride_j] + A.bt[row]) + s : s;
+                }
+            } else {
+                const T gd = T(-2) * d * A.grad_scores[pair];
+                const T re1 = re - T(1);
+                const T mod2 = Sc<T>::fma_(re1, re1, im * im);
+                const T sq = Sc<T>::sqrt_(x * x - T(1));
+                const T pz = Sc<T>::min_(sq * zn * zn * wn, -Sc<T>::ball_eps);
+                const T pw = Sc<T>::min_(sq * wn * wn * zn, -Sc<T>::ball_eps);
+                const T cz = T(4) * gd / pz, cw = T(4) * gd / pw;
+                T* grow = A.grad_rows + pair * 2 * r;
+                T* gqrow = per_pair_q ? A.grad_q + (b * A.q_stride_b + j * A.q_stride_j) * 2 * r : nullptr;
+#pragma unroll
+                for (int i = 0; i < NITER; ++i) {
+                    int k = lane + 32 * i;
+                    T a_r = cz * (zn * (re1 * wr[i] - im * wi[i]) - mod2 * zr[i]);
+                    T a_i = cz * (zn * (re1 * wi[i] + im * wr[i]) - mod2 * zi[i]);
+                    T b_r = cw * (wn * (re1 * zr[i] + im * zi[i]) - mod2 * wr[i]);
+                    T b_i = cw * (wn * (re1 * zi[i] - im * zr[i]) - mod2 * wi[i]);
+                    if (k < r) {
+                        grow[k] = b_r; grow[r + k] = b_i;
+                        if (per_pair_q) { gqrow[k] = a_r; gqrow[r + k] = a_i; }
+                    }
+                    gzr[i] += a_r; gzi[i] += a_i;
+                }
+            }
+        }
+        if (BWD && !per_pair_q) {
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < NITER; ++i) {
+                int k = lane + 32 * i;
+                if (k < r) { red[warp * 2 * r + k] = gzr[i]; red[warp * 2 * r + r + k] = gzi[i]; }
+            }
+            __syncthreads();
+            T* out = A.grad_q + b * A.q_stride_b * 2 * r;
+            for (int c = threadIdx.x; c < 2 * r; c += blockDim.x) {
+                T s = T(0);
+#pragma unroll
+                for (int w = 0; w < kWarps; ++w) s += red[w * 2 * r + c];
+                out[c] = s;
+            }
+        }
+    }
+}
+
+template <typename T, bool BWD>
+int launch_gather(const SArgs<T>& A, cudaStream_t st) {
+    int niter = (A.r + 31) / 32;
+    int64_t blocks = A.B < 148 * 32 ? A.B : 148 * 32;
+    size_t smem = BWD ? (size_t)kWarps * 2 * A.r * sizeof(T) : 0;
+#define CHK_LAUNCH(NI)                                                                              \
+    score_gather_kernel<T, NI, BWD><<<(unsigned)blocks, kWarps * 32, smem, st>>>(A)
+    if (niter <= 1) CHK_LAUNCH(1);
+    else if (niter <= 2) CHK_LAUNCH(2);
+    else if (niter <= 3) CHK_LAUNCH(3);
+    else if (niter <= 5) CHK_LAUNCH(5);
+    else if (niter <= 9) CHK_LAUNCH(9);
+    else { chk_set_error("rank %d too large", A.r); return CHK_EUNSUPPORTED; }
+#undef CHK_LAUNCH
+    CHK_CUDA_LAUNCH_CHECK("score_gather_kernel");
+    return CHK_OK;
+}
+
+template <typename T>
+__global__ void scatter_add_rows_kernel(T* __restrict__ dense, const int64_t* __restrict__ idx,
+                                        const T* __restrict__ rows, int64_t n_rows, int64_t width) {
+    const int64_t total = n_rows * width;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t rrow = i / width, c = i - rrow * width;
+        atomicAdd(dense + idx[rrow] * width + c, rows[i]);
+    }
+}
+
+}  // namespace
+
+extern "C" int chk_score_gather_fwd(int dtype, int rank, int64_t B, int64_t nt,
+                                    const void* q, int64_t q_stride_b, int64_t q_stride_j,
+                                    const void* table, const int64_t* tail_idx, int64_t row_stride_b,
+                                    const void* bh_vals, int64_t bh_stride_b, int64_t bh_stride_j, const void* bt,
+                                    void* scores, void* stream) {
+    if (B == 0 || nt == 0) return CHK_OK;
+    if (B < 0 || nt < 0 || rank < 2 || !q || !table || !scores) { chk_set_error("chk_score_gather_fwd: bad argument"); return CHK_EINVAL; }
+    if ((bh_vals == nullptr) != (bt == nullptr)) { chk_set_error("bh_vals and bt must both be given or both be NULL"); return CHK_EINVAL; }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == CHK_F32) {
+        SArgs<float> A{(const float*)q, q_stride_b, q_stride_j, (const float*)table, tail_idx, row_stride_b,
+                       (const float*)bh_vals, bh_stride_b, bh_stride_j, (const float*)bt, B, nt, rank, (float*)scores, nullptr, nullptr, nullptr};
+        return launch_gather<float, false>(A, st);
+    } else if (dtype == CHK_F64) {
+        SArgs<double> A{(const double*)q, q_stride_b, q_stride_j, (const double*)table, tail_idx, row_stride_b,
+                        (const double*)bh_vals, bh_stride_b, bh_stride_j, (const double*)bt, B, nt, rank, (double*)scores, nullptr, nullptr, nullptr};
+        return launch_gather<double, false>(A, st);
+    }
+    chk_set_error("unknown dtype %d", dtype); return CHK_EINVAL;
+}
+
+extern "C" int chk_score_gather_bwd(int dtype, int rank, int64_t B, int64_t nt,
+                                    const void* q, int64_t q_stride_b, int64_t q_stride_j,
+                                    const void* table, const int64_t* tail_idx, int64_t row_stride_b,
+                                    const void* grad_scores, void* grad_q, void* grad_rows, void* stream) {
+    if (B == 0 || nt == 0) return CHK_OK;
+    if (B < 0 || nt < 0 || rank < 2 || !q || !table || !grad_scores || !grad_q || !grad_rows) {
+        chk_set_error("chk_score_gather_bwd: bad argument"); return CHK_EINVAL;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == CHK_F32) {
+        SArgs<float> A{(const float*)q, q_stride_b, q_stride_j, (const float*)table, tail_idx, row_stride_b,
+                       nullptr, 0, 0, nullptr, B, nt, rank, nullptr, (const float*)grad_scores, (float*)grad_q, (float*)grad_rows};
+        return launch_gather<float, true>(A, st);
+    } else if (dtype == CHK_F64) {
+        SArgs<double> A{(const double*)q, q_stride_b, q_stride_j, (const double*)table, tail_idx, row_stride_b,
+                        nullptr, 0, 0, nullptr, B, nt, rank, nullptr, (const double*)grad_scores, (double*)grad_q, (double*)grad_rows};
+        return launch_gather<double, true>(A, st);
+    }
+    chk_set_error("unknown dtype %d", dtype); return CHK_EINVAL;
+}
+
+extern "C" int chk_scatter_add_rows(int dtype, void* dense, const int64_t* idx, const void* rows,
+                                    int64_t n_rows, int64_t width, void* stream) {
+    if (n_rows == 0 || width == 0) return CHK_OK;
+    if (n_rows < 0 || width < 0 || !dense || !idx || !rows) { chk_set_error("chk_scatter_add_rows: bad argument"); return CHK_EINVAL; }
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t total = n_rows * width;
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (dtype == CHK_F32) scatter_add_rows_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((float*)dense, idx, (const float*)rows, n_rows, width);
+    else if (dtype == CHK_F64) scatter_add_rows_kernel<double><<<(unsigned)blocks, 256, 0, st>>>((double*)dense, idx, (const double*)rows, n_rows, width);
+    else { chk_set_error("unknown dtype %d", dtype); return CHK_EINVAL; }
+    CHK_CUDA_LAUNCH_CHECK("scatter_add_rows_kernel");
+    return CHK_OK;
+}

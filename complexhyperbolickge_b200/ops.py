@@ -1,0 +1,289 @@
+"""Host wrappers + autograd Functions over the C ABI (include/chk_b200.h).
+
+PyTorch is plumbing here: it owns device memory and the CUDA stream, and autograd is only used to hand
+the kernels' analytic gradients to ``torch.optim`` so that the reference's training loop
+(optimizers/kg_optimizer.py:239-277) runs unchanged.  Every op requires CUDA tensors and raises otherwise.
+"""
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import CHK_ATT, CHK_F32, CHK_F64, CHK_RANK_FMA, CHK_RANK_MMA, CHK_REF, CHK_ROT  # noqa: F401
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return CHK_F32
+    if t.dtype == torch.float64:
+        return CHK_F64
+    raise TypeError(f"chk_b200 supports float32/float64 tables, got {t.dtype}")
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _chk(*tensors):
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("chk_b200 ops need CUDA tensors (there is no CPU fallback)")
+        if not t.is_contiguous():
+            raise RuntimeError("chk_b200 ops need contiguous tensors")
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def supported_rank(rank: int) -> bool:
+    n = 2 * (rank - 1)
+    return 16 <= n <= 512 and (n & (n - 1)) == 0
+
+
+# ------------------------------------------------------------------------------------------- raw calls
+def query_fwd(kind, rank, multi_c, entity, rel, rel_diag, ctx, c_table, head_idx, rel_idx):
+    _chk(entity, rel, rel_diag, ctx, c_table, head_idx, rel_idx)
+    nq = head_idx.numel()
+    q = torch.empty((nq, 2 * rank), dtype=entity.dtype, device=entity.device)
+    c = torch.empty((nq,), dtype=entity.dtype, device=entity.device)
+    _lib.check(_lib.lib().chk_query_fwd(kind, _dt(entity), rank, nq, int(multi_c), _p(entity), _p(rel), _p(rel_diag),
+                                        _p(ctx), _p(c_table), _p(head_idx), _p(rel_idx), _p(q), _p(c), _stream()),
+               "chk_query_fwd")
+    return q, c
+
+
+def query_bwd(kind, rank, multi_c, entity, rel, rel_diag, ctx, c_table, head_idx, rel_idx, grad_q):
+    _chk(entity, rel, rel_diag, ctx, c_table, head_idx, rel_idx, grad_q)
+    nq = head_idx.numel()
+    n = 2 * (rank - 1)
+    mk = lambda w: torch.empty((nq, w), dtype=entity.dtype, device=entity.device)
+    g_ent, g_rel, g_rd = mk(2 * rank), mk(2 * n), mk(2 * n if kind == CHK_ATT else n)
+    g_ctx = mk(n) if kind == CHK_ATT else None
+    g_c = mk(1)
+    _lib.check(_lib.lib().chk_query_bwd(kind, _dt(entity), rank, nq, int(multi_c), _p(entity), _p(rel), _p(rel_diag),
+                                        _p(ctx), _p(c_table), _p(head_idx), _p(rel_idx), _p(grad_q), _p(g_ent),
+                                        _p(g_rel), _p(g_rd), _p(g_ctx), _p(g_c), _stream()), "chk_query_bwd")
+    return g_ent, g_rel, g_rd, g_ctx, g_c
+
+
+def score_gather_fwd(rank, B, nt, q, q_stride_b, q_stride_j, table, tail_idx, row_stride_b, bh_vals, bh_sb, bh_sj, bt):
+    _chk(q, table, tail_idx, bh_vals, bt)
+    scores = torch.empty((B, nt), dtype=q.dtype, device=q.device)
+    _lib.check(_lib.lib().chk_score_gather_fwd(_dt(q), rank, B, nt, _p(q), q_stride_b, q_stride_j, _p(table),
+                                               _p(tail_idx), row_stride_b, _p(bh_vals), bh_sb, bh_sj, _p(bt),
+                                               _p(scores), _stream()), "chk_score_gather_fwd")
+    return scores
+
+
+def score_gather_bwd(rank, B, nt, q, q_stride_b, q_stride_j, table, tail_idx, row_stride_b, grad_scores):
+    _chk(q, table, tail_idx, grad_scores)
+    grad_q = torch.empty_like(q)
+    grad_rows = torch.empty((B * nt, 2 * rank), dtype=q.dtype, device=q.device)
+    _lib.check(_lib.lib().chk_score_gather_bwd(_dt(q), rank, B, nt, _p(q), q_stride_b, q_stride_j, _p(table),
+                                               _p(tail_idx), row_stride_b, _p(grad_scores), _p(grad_q),
+                                               _p(grad_rows), _stream()), "chk_score_gather_bwd")
+    return grad_q, grad_rows
+
+
+def scatter_add_rows(dense, idx, rows):
+    _chk(dense, idx, rows)
+    width = dense.shape[1] if dense.dim() > 1 else 1
+    n_rows = idx.numel()
+    assert rows.numel() == n_rows * width, (rows.shape, n_rows, width)
+    _lib.check(_lib.lib().chk_scatter_add_rows(_dt(dense), _p(dense), _p(idx), _p(rows), n_rows, width, _stream()),
+               "chk_scatter_add_rows")
+
+
+def row_hnorm(rank, table):
+    _chk(table)
+    n = table.shape[0]
+    out = torch.empty((n,), dtype=table.dtype, device=table.device)
+    _lib.check(_lib.lib().chk_row_hnorm(_dt(table), rank, n, _p(table), _p(out), _stream()), "chk_row_hnorm")
+    return out
+
+
+def score_all(rank, q, qn, bh_vals, entity, hn, bt):
+    _chk(q, qn, bh_vals, entity, hn, bt)
+    b, n = q.shape[0], entity.shape[0]
+    out = torch.empty((b, n), dtype=q.dtype, device=q.device)
+    _lib.check(_lib.lib().chk_score_all(_dt(q), rank, b, _p(q), _p(qn), _p(bh_vals), _p(entity), _p(hn), _p(bt), n,
+                                        _p(out), _stream()), "chk_score_all")
+    return out
+
+
+def target_scores(rank, q, qn, bh_vals, tail_rows, tail_hn, tail_bt):
+    _chk(q, qn, bh_vals, tail_rows, tail_hn, tail_bt)
+    b = q.shape[0]
+    out = torch.empty((b,), dtype=q.dtype, device=q.device)
+    _lib.check(_lib.lib().chk_target_scores(_dt(q), rank, b, _p(q), _p(qn), _p(bh_vals), _p(tail_rows), _p(tail_hn),
+                                            _p(tail_bt), _p(out), _stream()), "chk_target_scores")
+    return out
+
+
+def rank_counts(algo, rank, q, qn, bh_vals, target, entity, hn, bt, shard_offset, filter_indptr, filter_idx,
+                filter_total, counts, shadow=None, workspace=None):
+    _chk(q, qn, bh_vals, target, entity, hn, bt, filter_indptr, filter_idx, counts, shadow, workspace)
+    assert counts.dtype == torch.int64
+    ws_bytes = 0 if workspace is None else workspace.numel() * workspace.element_size()
+    _lib.check(_lib.lib().chk_rank_counts(algo, _dt(q), rank, q.shape[0], _p(q), _p(qn), _p(bh_vals), _p(target),
+                                          _p(entity), _p(hn), _p(bt), entity.shape[0], shard_offset,
+                                          _p(filter_indptr), _p(filter_idx), filter_total, _p(shadow), _p(workspace),
+                                          ws_bytes, _p(counts), _stream()), "chk_rank_counts")
+    return counts
+
+
+def entity_shadow(rank, entity):
+    """bf16 hi/lo planes of an fp32 entity table for the tcgen05 tier (TMA-legal, K padded)."""
+    _chk(entity)
+    nbytes = _lib.lib().chk_entity_shadow_bytes(rank, entity.shape[0])
+    if nbytes <= 0:
+        raise RuntimeError("CHK_RANK_MMA shadow unavailable: " + _lib.lib().chk_last_error().decode())
+    buf = torch.empty((nbytes,), dtype=torch.uint8, device=entity.device)
+    _lib.check(_lib.lib().chk_entity_shadow_build(rank, entity.shape[0], _p(entity), _p(buf), _stream()),
+               "chk_entity_shadow_build")
+    return buf
+
+
+def mma_available(rank: int = 257) -> bool:
+    """True when the tcgen05 tier (CHK_RANK_MMA) is built into the library."""
+    return _lib.lib().chk_entity_shadow_bytes(rank, 128) > 0
+
+
+def rank_mma_workspace(rank, b, device):
+    nbytes = _lib.lib().chk_rank_mma_workspace_bytes(rank, b)
+    return torch.zeros((max(nbytes, 16),), dtype=torch.uint8, device=device)
+
+
+# ------------------------------------------------------------------------------------------- autograd
+class QueryTransformFn(torch.autograd.Function):
+    """get_queries as ONE kernel forward and ONE kernel backward (reference: ~35 eager ops each way)."""
+
+    @staticmethod
+    def forward(ctx, meta, entity, rel, rel_diag, ctx_vec, c_table, head_idx, rel_idx):
+        kind, rank, multi_c = meta
+        q, c = query_fwd(kind, rank, multi_c, entity, rel, rel_diag, ctx_vec, c_table, head_idx, rel_idx)
+        ctx.meta = meta
+        ctx.save_for_backward(entity, rel, rel_diag, ctx_vec if ctx_vec is not None else entity.new_empty(0), c_table,
+                              head_idx, rel_idx)
+        ctx.has_ctx = ctx_vec is not None
+        ctx.mark_non_differentiable(c)       # the curvature rides along but Distance ignores it (complexhyperbolic.py:59)
+        return q, c
+
+    @staticmethod
+    def backward(ctx, grad_q, _grad_c):
+        kind, rank, multi_c = ctx.meta
+        entity, rel, rel_diag, ctx_vec, c_table, head_idx, rel_idx = ctx.saved_tensors
+        ctx_vec = ctx_vec if ctx.has_ctx else None
+        grads = query_param_grads(kind, rank, multi_c, entity, rel, rel_diag, ctx_vec, c_table, head_idx, rel_idx,
+                                  grad_q.contiguous(), None)
+        return (None, grads["entity"], grads["rel"], grads["rel_diag"], grads.get("context_vec"), grads["c"], None,
+                None)
+
+
+def query_param_grads(kind, rank, multi_c, entity, rel, rel_diag, ctx_vec, c_table, head_idx, rel_idx, grad_q,
+                      g_entity_dense):
+    """chk_query_bwd + scatter into DENSE parameter grads (what embedding_dense_backward leaves in .grad)."""
+    g_ent, g_rel, g_rd, g_ctx, g_c = query_bwd(kind, rank, multi_c, entity, rel, rel_diag, ctx_vec, c_table,
+                                               head_idx, rel_idx, grad_q)
+    out = {}
+    out["entity"] = torch.zeros_like(entity) if g_entity_dense is None else g_entity_dense
+    scatter_add_rows(out["entity"], head_idx, g_ent)
+    out["rel"] = torch.zeros_like(rel)
+    scatter_add_rows(out["rel"], rel_idx, g_rel)
+    out["rel_diag"] = torch.zeros_like(rel_diag)
+    scatter_add_rows(out["rel_diag"], rel_idx, g_rd)
+    if ctx_vec is not None:
+        out["context_vec"] = torch.zeros_like(ctx_vec)
+        scatter_add_rows(out["context_vec"], rel_idx, g_ctx)
+    out["c"] = torch.zeros_like(c_table)
+    if multi_c:
+        scatter_add_rows(out["c"], rel_idx, g_c)
+    else:
+        out["c"] += g_c.sum()
+    return out
+
+
+class ScoreRowsFn(torch.autograd.Function):
+    """similarity_score on explicit tensors: q [B,1|nt,2r] vs rhs rows [B,nt,2r] or [1,nt,2r] (no bias)."""
+
+    @staticmethod
+    def forward(ctx, rank, q, rhs):
+        B = max(q.shape[0], rhs.shape[0])
+        nt = max(q.shape[1], rhs.shape[1])
+        q2 = q.expand(B, q.shape[1], 2 * rank).contiguous()
+        qsj = 1 if q.shape[1] > 1 else 0
+        qsb = q2.shape[1]
+        rsb = nt if rhs.shape[0] > 1 else 0
+        if rhs.shape[1] != nt:
+            rhs = rhs.expand(rhs.shape[0], nt, 2 * rank)
+        table = rhs.contiguous().view(-1, 2 * rank)
+        scores = score_gather_fwd(rank, B, nt, q2.view(-1, 2 * rank), qsb, qsj, table, None, rsb, None, 0, 0, None)
+        ctx.cfg = (rank, B, nt, qsb, qsj, rsb, tuple(q.shape), tuple(rhs.shape))
+        ctx.save_for_backward(q2, table)
+        return scores.unsqueeze(-1)
+
+    @staticmethod
+    def backward(ctx, grad):
+        rank, B, nt, qsb, qsj, rsb, qshape, rshape = ctx.cfg
+        q2, table = ctx.saved_tensors
+        gq, grows = score_gather_bwd(rank, B, nt, q2.view(-1, 2 * rank), qsb, qsj, table, None, rsb,
+                                     grad.reshape(B, nt).contiguous())
+        gq = gq.view(B, -1, 2 * rank)
+        if qshape[0] == 1 and B > 1:
+            gq = gq.sum(0, keepdim=True)
+        grows = grows.view(B, nt, 2 * rank)
+        if rshape[0] == 1 and B > 1:
+            grows = grows.sum(0, keepdim=True)
+        return None, gq, grows
+
+
+class FusedForwardFn(torch.autograd.Function):
+    """KGModel.forward(queries, tails) for the negative-sampling loss: K1 + gather-scoring in two kernels,
+    backward = scoring adjoint -> query adjoint -> one dense scatter (reference: two eager graphs through
+    get_queries / get_rhs / score, models/base.py:200-226)."""
+
+    @staticmethod
+    def forward(ctx, meta, entity, rel, rel_diag, ctx_vec, c_table, bh, bt, queries, tails):
+        kind, rank, multi_c, learn_bias = meta
+        B, nq1 = queries.shape[0], queries.shape[1]
+        nt = tails.shape[1]
+        head_idx = queries[..., 0].reshape(-1).contiguous()
+        rel_idx = queries[..., 1].reshape(-1).contiguous()
+        tails = tails.contiguous()
+        q, _ = query_fwd(kind, rank, multi_c, entity, rel, rel_diag, ctx_vec, c_table, head_idx, rel_idx)
+        qsj = 1 if nq1 > 1 else 0
+        if learn_bias:
+            bh_vals = bh.view(-1)[head_idx].contiguous()
+            scores = score_gather_fwd(rank, B, nt, q, nq1, qsj, entity, tails, 0, bh_vals, nq1, qsj, bt.view(-1))
+        else:
+            scores = score_gather_fwd(rank, B, nt, q, nq1, qsj, entity, tails, 0, None, 0, 0, None)
+        ctx.meta = meta
+        ctx.dims = (B, nq1, nt, qsj)
+        ctx.has_ctx = ctx_vec is not None
+        ctx.save_for_backward(entity, rel, rel_diag, ctx_vec if ctx_vec is not None else entity.new_empty(0), c_table,
+                              bh, bt, head_idx, rel_idx, tails, q)
+        return scores.unsqueeze(-1)
+
+    @staticmethod
+    def backward(ctx, grad):
+        kind, rank, multi_c, learn_bias = ctx.meta
+        B, nq1, nt, qsj = ctx.dims
+        entity, rel, rel_diag, ctx_vec, c_table, bh, bt, head_idx, rel_idx, tails, q = ctx.saved_tensors
+        ctx_vec = ctx_vec if ctx.has_ctx else None
+        g = grad.reshape(B, nt).contiguous()
+        grad_q, grad_rows = score_gather_bwd(rank, B, nt, q, nq1, qsj, entity, tails, 0, g)
+        g_entity = torch.zeros_like(entity)
+        scatter_add_rows(g_entity, tails.view(-1), grad_rows)
+        grads = query_param_grads(kind, rank, multi_c, entity, rel, rel_diag, ctx_vec, c_table, head_idx, rel_idx,
+                                  grad_q, g_entity)
+        g_bh = g_bt = None
+        if learn_bias:
+            g_bh, g_bt = torch.zeros_like(bh), torch.zeros_like(bt)
+            gh = g if qsj else g.sum(1)
+            scatter_add_rows(g_bh, head_idx, gh.contiguous())
+            scatter_add_rows(g_bt, tails.view(-1), g)
+        return (None, grads["entity"], grads["rel"], grads["rel_diag"], grads.get("context_vec"), grads["c"], g_bh,
+                g_bt, None, None)

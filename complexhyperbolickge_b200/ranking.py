@@ -1,0 +1,91 @@
+"""Filtered full ranking driver: K1 -> target scores -> fused rank counts (-> all_reduce when sharded).
+
+Replaces the body of KGModel.get_ranking (reference models/base.py:239-280).  Multi-GPU:
+the entity table is row-sharded into contiguous ranges, one per rank of ``model.process_group``; the query
+transform and the target scores are computed redundantly on every rank (bit-identical), each rank counts
+over its shard and the int64 counts are summed with ONE all_reduce per ranking pass — the only collective
+on the path.  Integer sums make the result independent of the number of shards.
+"""
+import numpy as np
+import torch
+
+from . import ops
+from .filters import FilterIndex
+
+
+def shard_bounds(n_rows: int, world: int, rank: int):
+    """Contiguous, balanced row ranges; tile-aligned (multiple of 128 rows) so the kernels see full tiles."""
+    per = (n_rows + world - 1) // world
+    per = (per + 127) // 128 * 128
+    lo = min(rank * per, n_rows)
+    hi = min(lo + per, n_rows)
+    return lo, hi
+
+
+class EvalState:
+    """Per-pass state: the rank's shard view, its Hermitian norms and (mma tier) the bf16 shadow."""
+
+    def __init__(self, model):
+        import torch.distributed as dist
+        pg = model.process_group
+        self.world = dist.get_world_size(pg) if pg is not None else 1
+        self.rank_id = dist.get_rank(pg) if pg is not None else 0
+        N = model.sizes[0]
+        self.lo, self.hi = shard_bounds(N, self.world, self.rank_id)
+        ent = model.entity.weight.detach()
+        self.entity = ent[self.lo:self.hi].contiguous()
+        self.bt = model.bt.weight.detach().view(-1)[self.lo:self.hi].contiguous() if model.bias == "learn" else None
+        self.hn = ops.row_hnorm(model.rank, self.entity) if self.hi > self.lo else ent.new_empty(0)
+        self.algo = ops.CHK_RANK_MMA if model.rank_algo == "mma" else ops.CHK_RANK_FMA
+        self.shadow = None
+        if self.algo == ops.CHK_RANK_MMA:
+            if ent.dtype != torch.float32:
+                raise RuntimeError("rank_algo='mma' is fp32 only (tcgen05 has no f64 kind); use 'fma' for --dtype double")
+            self.shadow = ops.entity_shadow(model.rank, self.entity) if self.hi > self.lo else None
+
+
+def rank_batch(model, state: EvalState, queries_dev: torch.Tensor, indptr_dev, idx_dev, filter_total: int,
+               counts: torch.Tensor, workspace=None):
+    """One evaluation batch on device; counts (int64 [b]) is accumulated in place."""
+    r = model.rank
+    head_idx = queries_dev[:, 0].contiguous()
+    rel_idx = queries_dev[:, 1].contiguous()
+    tails = queries_dev[:, 2].contiguous()
+    ctxw = model._ctx_weight()
+    q, _ = ops.query_fwd(model.KIND, r, bool(model.multi_c), model.entity.weight.detach(), model.rel.weight.detach(),
+                         model.rel_diag.weight.detach(), None if ctxw is None else ctxw.detach(),
+                         model.c.weight.detach(), head_idx, rel_idx)
+    qn = ops.row_hnorm(r, q)
+    learn = model.bias == "learn"
+    bh_vals = model.bh.weight.detach().view(-1)[head_idx].contiguous() if learn else None
+    tail_rows = model.entity.weight.detach()[tails].contiguous()
+    tail_bt = model.bt.weight.detach().view(-1)[tails].contiguous() if learn else None
+    target = ops.target_scores(r, q, qn, bh_vals, tail_rows, ops.row_hnorm(r, tail_rows), tail_bt)
+    if state.hi > state.lo:
+        ops.rank_counts(state.algo, r, q, qn, bh_vals, target, state.entity, state.hn, state.bt, state.lo,
+                        indptr_dev, idx_dev, filter_total, counts, state.shadow, workspace)
+    return target
+
+
+def rank_queries(model, queries: torch.Tensor, findex: FilterIndex, batch_size: int) -> torch.Tensor:
+    dev = model.entity.weight.device
+    if dev.type != "cuda":
+        raise RuntimeError("complexhyperbolickge_b200 models run on CUDA only (no CPU fallback)")
+    n = queries.shape[0]
+    q_np = queries.cpu().numpy() if isinstance(queries, torch.Tensor) else np.asarray(queries)
+    counts_all = torch.zeros(n, dtype=torch.int64, device=dev)
+    with torch.no_grad():
+        state = EvalState(model)
+        ws = ops.rank_mma_workspace(model.rank, batch_size, dev) if state.algo == ops.CHK_RANK_MMA else None
+        for b0 in range(0, n, batch_size):
+            qb = q_np[b0:b0 + batch_size]
+            indptr, idx = findex.batch_csr(qb)
+            qd = torch.from_numpy(np.ascontiguousarray(qb)).to(dev, non_blocking=True)
+            ip = torch.from_numpy(indptr).to(dev, non_blocking=True)
+            ix = torch.from_numpy(idx).to(dev, non_blocking=True) if idx.size else torch.zeros(1, dtype=torch.int64, device=dev)
+            target = rank_batch(model, state, qd, ip, ix, int(idx.size), counts_all[b0:b0 + batch_size], ws)
+            assert not torch.isnan(target).any()          # models/base.py:259-260
+        if state.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(counts_all, op=dist.ReduceOp.SUM, group=model.process_group)
+    return (counts_all + 1).to(torch.float32).cpu()

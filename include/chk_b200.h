@@ -1,0 +1,129 @@
+/* chk_b200.h — C ABI of the B200-native FFTRotH / FFTRefH / FFTAttH scoring hot path.
+ *
+ * Drop-in boundary for htmai-880/ComplexHyperbolicKGE (reference paths are relative to its root).
+ * Every entry point replaces a piece of the reference's eager-PyTorch code that a binding
+ * (ctypes) would call instead.  Conventions:
+ *   - all pointers are DEVICE pointers (cudaMalloc'ed / torch CUDA tensors), contiguous, row-major;
+ *   - `dtype` = CHK_F32 | CHK_F64 selects the scalar type of every `void*` table / vector
+ *     (models/base.py:35-39 `--dtype float|double`); indices are int64 (torch.LongTensor);
+ *   - `rank` r: entity rows are 2r wide = [Re X_0..X_{r-1} | Im X_0..X_{r-1}]; n = 2(r-1) must be a
+ *     power of two with 16 <= n <= 512 (r in {9,17,33,65,129,257});
+ *   - `stream` is a cudaStream_t (the caller's current stream); launches are asynchronous;
+ *   - the library never allocates or frees memory it returns, holds no mutable global state besides the
+ *     per-thread last-error string, and never calls back into the host language;
+ *   - return value 0 = success, otherwise a CHK_E* code; chk_last_error() gives the text.
+ * There is NO CPU fallback: without a CUDA device every compute entry returns CHK_ECUDA.
+ */
+#ifndef CHK_B200_H
+#define CHK_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { CHK_ROT = 0, CHK_REF = 1, CHK_ATT = 2 };          /* FFTRotH / FFTRefH / FFTAttH */
+enum { CHK_F32 = 0, CHK_F64 = 1 };
+enum { CHK_OK = 0, CHK_EINVAL = 1, CHK_ECUDA = 2, CHK_EUNSUPPORTED = 3, CHK_EOVERFLOW = 4 };
+enum { CHK_RANK_FMA = 0, CHK_RANK_MMA = 1 };             /* chk_rank_counts algorithm */
+
+int chk_abi_version(void);
+const char* chk_last_error(void);
+
+/* ---- K1: query transform (get_queries) --------------------------------------------------------
+ * Replaces FFTRotH/FFTRefH/FFTAttH.get_queries (models/complexhyperbolic.py:79-101,107-127,144-171):
+ * irfft -> expmap0 -> Moebius translation -> Givens rotation / "reflection" / attention -> rfft, with
+ * utils/complexhyperbolic.py:41-54,72-106 and utils/euclidean.py:26-75 fused, one warp per query.
+ * c_table is c.weight: (R2,1) raw (softplus applied inside) when multi_c, else (1,1) used RAW.
+ * out_q [nq,2r], out_c [nq] (the curvature actually used).  ctx may be NULL unless kind==CHK_ATT. */
+int chk_query_fwd(int kind, int dtype, int rank, int64_t nq, int multi_c,
+                  const void* entity, const void* rel, const void* rel_diag, const void* ctx,
+                  const void* c_table, const int64_t* head_idx, const int64_t* rel_idx,
+                  void* out_q, void* out_c, void* stream);
+
+/* Adjoint of chk_query_fwd (what autograd does through the ~35 eager ops of get_queries).
+ * grad_q [nq,2r] in; per-query gradient ROWS out (the caller scatters them with chk_scatter_add_rows):
+ * g_entity_rows [nq,2r], g_rel_rows [nq,2n], g_rel_diag_rows [nq,n] ([nq,2n] for ATT),
+ * g_ctx_rows [nq,n] (ATT only, else NULL), g_c [nq] (w.r.t. the RAW c parameter). */
+int chk_query_bwd(int kind, int dtype, int rank, int64_t nq, int multi_c,
+                  const void* entity, const void* rel, const void* rel_diag, const void* ctx,
+                  const void* c_table, const int64_t* head_idx, const int64_t* rel_idx,
+                  const void* grad_q,
+                  void* g_entity_rows, void* g_rel_rows, void* g_rel_diag_rows, void* g_ctx_rows,
+                  void* g_c, void* stream);
+
+/* ---- K3: scoring of gathered tails, forward + backward (training / similarity_score) -----------
+ * Replaces KGModel.get_rhs + score + FFTUnitBall.similarity_score + Distance.forward/backward
+ * (models/base.py:108-133,148-173; models/complexhyperbolic.py:45-59;
+ *  utils/complexhyperbolic.py:176-254, lift=True semantics) for B queries x nt tails.
+ * q row of pair (b,j) = q + (b*q_stride_b + j*q_stride_j)*2r   (q_stride_j = 0: one query per b).
+ * tail row of pair (b,j) = table[tail_idx[b*nt+j]] if tail_idx else table[b*row_stride_b + j].
+ * scores[b*nt+j] = (bh_vals[b*bh_stride_b + j*bh_stride_j] + bt[row]) + (-acosh(x)^2); bh_vals/bt may
+ * both be NULL (bias none). */
+int chk_score_gather_fwd(int dtype, int rank, int64_t B, int64_t nt,
+                         const void* q, int64_t q_stride_b, int64_t q_stride_j,
+                         const void* table, const int64_t* tail_idx, int64_t row_stride_b,
+                         const void* bh_vals, int64_t bh_stride_b, int64_t bh_stride_j, const void* bt,
+                         void* scores, void* stream);
+
+/* grad_scores [B,nt] -> grad_q rows (same strides as q; must be pre-zeroed by the caller only if
+ * q_stride_j==0 is NOT used — when q_stride_j==0 the kernel reduces over j and overwrites row b) and
+ * grad_rows [B*nt,2r] (one row per pair, to be scattered by the caller).  Straight-through at the
+ * clamps exactly as Distance.backward (utils/complexhyperbolic.py:202-203,231-234). */
+int chk_score_gather_bwd(int dtype, int rank, int64_t B, int64_t nt,
+                         const void* q, int64_t q_stride_b, int64_t q_stride_j,
+                         const void* table, const int64_t* tail_idx, int64_t row_stride_b,
+                         const void* grad_scores,
+                         void* grad_q, void* grad_rows, void* stream);
+
+/* dense[idx[i], :] += rows[i, :]   (embedding_dense_backward of entity/rel/bias tables). */
+int chk_scatter_add_rows(int dtype, void* dense, const int64_t* idx, const void* rows,
+                         int64_t n_rows, int64_t width, void* stream);
+
+/* ---- K2: scoring against the whole entity table + filtered rank counts (evaluation) -------------
+ * All K2 entry points share ONE canonical pair-score arithmetic (ascending-k FMA chain, see
+ * csrc/chk_common.cuh) so that target scores, tile counts, the filter pass and the exact re-check of the
+ * tensor-core tier agree bit-for-bit; exact ties (clamp regime) therefore behave like the reference's.
+ *
+ * Clamped Hermitian norm of every row: hn[i] = clamp(sum|w_i|^2 - 1, -1, -eps)
+ * (utils/complexhyperbolic.py:187-188,229-230).  Used for the entity table (once per evaluation pass)
+ * and for the query batch (qn). */
+int chk_row_hnorm(int dtype, int rank, int64_t n_rows, const void* table, void* hn, void* stream);
+
+/* scores[i, e] for all e in the shard (models/base.py:255 `score(q, candidates)`).  q [b,2r], qn [b],
+ * hn/bt [n_rows]; bh_vals/bt both NULL for bias 'none'.  scores [b, n_rows]. */
+int chk_score_all(int dtype, int rank, int64_t b, const void* q, const void* qn, const void* bh_vals,
+                  const void* entity, const void* hn, const void* bt, int64_t n_rows,
+                  void* scores, void* stream);
+
+/* target[i] = score(q_i, tail_rows_i) (models/base.py:256).  tail_rows [b,2r], tail_hn [b], tail_bt [b]
+ * are the gathered rows of the true tails (gathered by the caller so that a sharded table works). */
+int chk_target_scores(int dtype, int rank, int64_t b, const void* q, const void* qn, const void* bh_vals,
+                      const void* tail_rows, const void* tail_hn, const void* tail_bt,
+                      void* target, void* stream);
+
+/* Filtered rank counts of KGModel.get_ranking (models/base.py:255-271), fused: for query i
+ *   counts[i] += #{ e in shard, e not in filter_i : score(i,e) >= target[i] }
+ * filter_i = filter_idx[filter_indptr[i] .. filter_indptr[i+1]) holds GLOBAL entity ids, UNIQUE per
+ * query, and must contain the true tail (the reference appends it, base.py:267); filter_total =
+ * filter_indptr[b].  Shard rows are global ids [shard_offset, shard_offset + n_rows).  counts is int64 [b],
+ * accumulated (caller zeroes it); summing it over shards / GPUs gives rank - 1.
+ * algo = CHK_RANK_FMA: exact fp32/fp64 FMA tiles.
+ * algo = CHK_RANK_MMA (fp32 only): tcgen05 bf16x3 tiles decide every pair whose score is outside a proven
+ *   error band around the target and the pairs inside the band are re-scored with the exact chain, so the
+ *   counts equal CHK_RANK_FMA's; needs the shadow from chk_entity_shadow_build and a workspace of
+ *   chk_rank_mma_workspace_bytes(rank, b) bytes (returns CHK_EOVERFLOW if the band list overflows). */
+int chk_rank_counts(int algo, int dtype, int rank, int64_t b, const void* q, const void* qn,
+                    const void* bh_vals, const void* target, const void* entity, const void* hn,
+                    const void* bt, int64_t n_rows, int64_t shard_offset,
+                    const int64_t* filter_indptr, const int64_t* filter_idx, int64_t filter_total,
+                    const void* shadow, void* workspace, int64_t workspace_bytes,
+                    int64_t* counts, void* stream);
+int64_t chk_entity_shadow_bytes(int rank, int64_t n_rows);
+int chk_entity_shadow_build(int rank, int64_t n_rows, const void* entity_f32, void* shadow, void* stream);
+int64_t chk_rank_mma_workspace_bytes(int rank, int64_t b);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

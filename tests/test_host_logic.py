@@ -1,0 +1,102 @@
+"""CPU: host-side logic (filter CSR, shard bounds, model construction / state_dict layout) and the C-ABI
+surface (library loads, every symbol declared in include/chk_b200.h is exported).  No compute calls."""
+import ctypes
+import os
+import re
+from argparse import Namespace
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, filters_from_arrays, golden_files, load_case
+
+
+def test_capi_exports_every_declared_symbol():
+    from complexhyperbolickge_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "chk_b200.h")).read()
+    declared = set(re.findall(r"\b(chk_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    if not os.path.exists(_lib.LIB_PATH):
+        _lib.build_native()
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(L, name), f"{name} declared in include/chk_b200.h but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert _lib.lib().chk_abi_version() == 1
+
+
+def test_no_cpu_fallback():
+    from complexhyperbolickge_b200 import ops
+    with pytest.raises(RuntimeError):
+        ops.row_hnorm(9, torch.zeros(4, 18))
+    import complexhyperbolickge_b200 as chk
+    m = chk.FFTRotH(Namespace(sizes=(10, 2, 10), rank=9, dropout=0, gamma=0, dtype="float", bias="learn",
+                              init_size=1e-3, multi_c=True))
+    with pytest.raises(RuntimeError):
+        m.get_queries(torch.zeros((2, 2), dtype=torch.int64))
+    with pytest.raises(RuntimeError):
+        m.get_ranking(torch.zeros((1, 3), dtype=torch.int64), {(0, 0): [0]}, 4)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "complexhyperbolickge_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle|import_module\([\"']oracle|oracle/", txt, re.M), f
+
+
+@pytest.mark.parametrize("name", ["FFTRotH", "FFTRefH", "FFTAttH"])
+@pytest.mark.parametrize("multi_c", [True, False])
+def test_state_dict_layout_matches_reference(name, multi_c):
+    """SURVEY §5 checkpoint row: keys and shapes must be interchangeable with the reference's model.pt."""
+    import complexhyperbolickge_b200 as chk
+    N, R2, r = 30, 6, 9
+    m = getattr(chk, name)(Namespace(sizes=(N, R2, N), rank=r, dropout=0, gamma=0, dtype="double", bias="learn",
+                                     init_size=1e-3, multi_c=multi_c))
+    n = 2 * (r - 1)
+    want = {"entity.weight": (N, 2 * r), "rel.weight": (R2, 2 * n), "rel_diag.weight": (R2, 2 * n if name == "FFTAttH" else n),
+            "c.weight": (R2 if multi_c else 1, 1), "bh.weight": (N, 1), "bt.weight": (N, 1)}
+    if name == "FFTAttH":
+        want["context_vec.weight"] = (R2, n)
+    got = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    assert got == want
+    assert all(v.dtype == torch.float64 for v in m.state_dict().values())
+    # golden fixture (reference state_dict) loads strictly
+    case = load_case([p for p in golden_files("step_" + name) if f"mc{int(multi_c)}" in p and "double" in p][0])
+    m2 = getattr(chk, name)(Namespace(sizes=(case["n_ent"], case["n_rel2"], case["n_ent"]), rank=case["rank"], dropout=0,
+                                      gamma=0, dtype="double", bias="learn", init_size=1e-3, multi_c=multi_c))
+    m2.load_state_dict({k[2:] + ".weight": torch.from_numpy(v) for k, v in case.items() if k.startswith("p_")})
+
+
+def test_filter_index_matches_reference_semantics():
+    from complexhyperbolickge_b200.filters import FilterIndex
+    case = load_case(golden_files("rank_FFTRotH_double_trained")[0])
+    filters = filters_from_arrays(case)
+    fi = FilterIndex.from_dict(filters["rhs"], case["n_rel2"])
+    fa = FilterIndex.from_arrays(case["rhs_keys"], case["rhs_indptr"], case["rhs_vals"], case["n_rel2"])
+    qs = case["test"][:57]
+    for f in (fi, fa):
+        indptr, idx = f.batch_csr(qs)
+        assert indptr.shape == (58,) and indptr[-1] == idx.size
+        for i, (h, r, t) in enumerate(qs):
+            want = sorted(set(filters["rhs"][(int(h), int(r))]) | {int(t)})      # base.py:266-267, deduplicated
+            assert idx[indptr[i]:indptr[i + 1]].tolist() == want
+    with pytest.raises(KeyError):
+        fi.batch_csr(np.array([[10 ** 6, 0, 1]]))
+    # ragged: empty filter dict, strict off -> just the targets
+    e = FilterIndex.from_dict({}, 4)
+    indptr, idx = e.batch_csr(np.array([[1, 2, 3], [4, 1, 0]]), strict=False)
+    assert indptr.tolist() == [0, 1, 2] and idx.tolist() == [3, 0]
+
+
+def test_shard_bounds_partition():
+    from complexhyperbolickge_b200.ranking import shard_bounds
+    for n in (1, 127, 128, 40943, 4_000_000):
+        for w in (1, 2, 4, 8):
+            spans = [shard_bounds(n, w, r) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+            assert all(lo % 128 == 0 or lo == n for lo, _ in spans)
