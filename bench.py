@@ -325,6 +325,7 @@ def run_ours(args):
         k1.record()
         torch.cuda.synchronize()
         kern_ms = k0.elapsed_time(k1) / nrep
+        recheck = ops.rank_mma_status(ws) if ws is not None else (0, False)
 
     # ---- e2e through the public API with host buffers
     e2e = None
@@ -366,9 +367,9 @@ def run_ours(args):
     achieved = flops / (kern_ms * 1e-3) / 1e12
     mma = state.algo == ops.CHK_RANK_MMA
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                "traffic": None, "kernel": "rank_mma_kernel (tcgen05 bf16x3)" if mma else "rank_tile_kernel<float,1> (fp32 FMA)",
+                "traffic": None, "kernel": "rank_mma_kernel (tcgen05 bf16x3, incl. operand prep + exact re-check)" if mma else "rank_tile_kernel<float,1> (fp32 FMA)",
                 "kernel_ms": kern_ms, "algorithmic_flop_per_pair": 8 * rank, "issued_flop_per_pair": 8 * rank * (3 if mma else 1),
-                "pairs_per_launch": b * shard_rows,
+                "pairs_per_launch": b * shard_rows, "recheck_pairs_per_launch": recheck[0], "recheck_overflow": recheck[1],
                 "peak_source": ("MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone)" if peaks else "fallback 1.59 PFLOP/s")}
     line = {"metric": METRIC, "value": b * K / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,

@@ -29,6 +29,8 @@ template <> struct Sc<float> {
     __device__ static __forceinline__ float exp_(float x) { return expf(x); }
     __device__ static __forceinline__ float log1p_(float x) { return log1pf(x); }
     __device__ static __forceinline__ float fma_(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+    __device__ static __forceinline__ float mul_(float a, float b) { return __fmul_rn(a, b); }   // never contracted
+    __device__ static __forceinline__ float add_(float a, float b) { return __fadd_rn(a, b); }
     __device__ static __forceinline__ float max_(float a, float b) { return fmaxf(a, b); }
     __device__ static __forceinline__ float min_(float a, float b) { return fminf(a, b); }
     __device__ static __forceinline__ float abs_(float a) { return fabsf(a); }
@@ -42,6 +44,8 @@ template <> struct Sc<double> {
     __device__ static __forceinline__ double exp_(double x) { return exp(x); }
     __device__ static __forceinline__ double log1p_(double x) { return log1p(x); }
     __device__ static __forceinline__ double fma_(double a, double b, double c) { return __fma_rn(a, b, c); }
+    __device__ static __forceinline__ double mul_(double a, double b) { return __dmul_rn(a, b); }
+    __device__ static __forceinline__ double add_(double a, double b) { return __dadd_rn(a, b); }
     __device__ static __forceinline__ double max_(double a, double b) { return fmax(a, b); }
     __device__ static __forceinline__ double min_(double a, double b) { return fmin(a, b); }
     __device__ static __forceinline__ double abs_(double a) { return fabs(a); }
@@ -95,11 +99,18 @@ __device__ __forceinline__ T acosh_x(T x) {
 }
 
 // score = (bh + bt) + (-d^2)  in that order (models/base.py:171); has_bias==false -> -d^2.
+// The square and the two adds are separately rounded (mul_/add_ are never contracted into an FMA), as
+// in the reference's eager ops, and so that every kernel produces the same bits from the same (x, bh, bt).
+template <typename T>
+__device__ __forceinline__ T score_from_x(T x, bool has_bias, T bh, T bt) {
+    T d = acosh_x(x);
+    T s = -Sc<T>::mul_(d, d);
+    return has_bias ? Sc<T>::add_(Sc<T>::add_(bh, bt), s) : s;
+}
+
 template <typename T>
 __device__ __forceinline__ T pair_score(T re, T im, T zn, T wn, bool has_bias, T bh, T bt) {
-    T d = acosh_x(clamped_x(re, im, zn, wn));
-    T s = -(d * d);
-    return has_bias ? (bh + bt) + s : s;
+    return score_from_x<T>(clamped_x(re, im, zn, wn), has_bias, bh, bt);
 }
 
 // Canonical dot chain over complex index k (zr,zi,wr,wi are the four real planes of the two rows).
@@ -110,3 +121,21 @@ __device__ __forceinline__ void dot_step(T zr, T zi, T wr, T wi, T& re, T& im) {
     im = Sc<T>::fma_(zi, wr, im);
     im = Sc<T>::fma_(-zr, wi, im);
 }
+
+// ---- exact per-pair score (canonical chain, one thread per pair) -----------------------------------
+template <typename T>
+__device__ __forceinline__ T exact_pair(const T* __restrict__ z, const T* __restrict__ w, int r, T zn, T wn,
+                                        bool has_bias, T bh, T bt) {
+    T re = T(0), im = T(0);
+    for (int k = 0; k < r; ++k) dot_step<T>(z[k], z[r + k], w[k], w[r + k], re, im);
+    return pair_score<T>(re, im, zn, wn, has_bias, bh, bt);
+}
+
+// Arguments shared by the K2 kernels (exact tier, filter pass, tensor-core tier re-check).
+template <typename T> struct RArgs {
+    const T* q; const T* qn; const T* bh_vals; const T* target;
+    const T* entity; const T* hn; const T* bt;
+    int64_t b, n_rows; int r;
+    T* scores;                       // MODE 0: [b, n_rows]
+    unsigned long long* counts;      // MODE 1: [b]
+};

@@ -36,14 +36,6 @@ template <typename T> struct TileCfg;
 template <> struct TileCfg<float>  { static constexpr int TQ = 8, TE = 4, KC = 16; };
 template <> struct TileCfg<double> { static constexpr int TQ = 4, TE = 4, KC = 16; };
 
-template <typename T> struct RArgs {
-    const T* q; const T* qn; const T* bh_vals; const T* target;
-    const T* entity; const T* hn; const T* bt;
-    int64_t b, n_rows; int r;
-    T* scores;                       // MODE 0: [b, n_rows]
-    unsigned long long* counts;      // MODE 1: [b]
-};
-
 template <typename T, int MODE>
 __global__ void __launch_bounds__(256) rank_tile_kernel(RArgs<T> A) {
     using C = TileCfg<T>;
@@ -151,14 +143,7 @@ __global__ void __launch_bounds__(256) rank_tile_kernel(RArgs<T> A) {
     }
 }
 
-// ---- per-pair exact kernels (canonical chain, one thread per pair) ---------------------------------
-template <typename T>
-__device__ __forceinline__ T exact_pair(const T* __restrict__ z, const T* __restrict__ w, int r, T zn, T wn,
-                                        bool has_bias, T bh, T bt) {
-    T re = T(0), im = T(0);
-    for (int k = 0; k < r; ++k) dot_step<T>(z[k], z[r + k], w[k], w[r + k], re, im);
-    return pair_score<T>(re, im, zn, wn, has_bias, bh, bt);
-}
+// ---- per-pair exact kernels (canonical chain exact_pair(), one thread per pair) ---------------------
 
 // target[i] = score(q_i, tail_rows_i)
 template <typename T>

@@ -1,16 +1,584 @@
-// K2 (tensor-core tier) — placeholder until the tcgen05 kernel lands; fails loudly, never falls back.
+// K2 (tensor-core tier) — filtered rank counts with the Hermitian contraction on tcgen05 (sm_100a only).
+//
+// Same contract as the exact tier (chk_rank.cu; reference models/base.py:243-271 + Distance.forward,
+// utils/complexhyperbolic.py:212-237) and the SAME integer counts, by filter-and-refine:
+//
+//   1. The complex contraction  <z_i, w_e> = sum_k z_ik conj(w_ek)  is a real GEMM
+//          D[e, 2i]   = sum_k w_e[k] * qre_i[k]      qre_i = [ Re z_i |  Im z_i ]
+//          D[e, 2i+1] = sum_k w_e[k] * qim_i[k]      qim_i = [ Im z_i | -Re z_i ]      (K = 2r)
+//      run as tcgen05.mma kind::f16 on bf16 operands with fp32 accumulation in TMEM.  fp32 inputs are split
+//      a = hi + lo (hi = bf16(a), lo = bf16(a - hi)) and three products hi*hi + hi*lo + lo*hi are
+//      accumulated into the same TMEM tile ("bf16x3": per-product error <= 2^-16 |a||b|).
+//      UMMA M = 128 entity rows (TMEM lanes), N = 256 query rows (= 128 queries, TMEM columns).
+//   2. Operands arrive through the TMA engine as 1-D bulk copies (cp.async.bulk + mbarrier complete_tx)
+//      of PRE-TILED blocks: the entity table has a bf16 hi/lo shadow (built once per evaluation pass,
+//      chk_entity_shadow_build) whose blocks are byte images of the shared-memory operand tile in the
+//      canonical no-swizzle K-major UMMA layout (8-row x 16-byte core matrices), so one 16 KB copy per
+//      stage feeds the entity side and one 32 KB copy the query side.  4-stage full/empty mbarrier ring,
+//      one elected producer thread, one elected MMA-issuer thread, accumulators double-buffered in TMEM
+//      (2 x 256 columns) so the epilogue of tile t overlaps the MMAs of tile t+1.
+//   3. Epilogue (8 warps, tcgen05.ld 32x32b): per pair an APPROXIMATE score s~ (MUFU rsqrt / lg2) and a
+//      proven bound Delta >= |s~ - s_exact| on its distance to the exact tier's fp32 score (split error,
+//      accumulation error of both tiers by Cauchy-Schwarz with the row norms, evaluation roundoff, and
+//      |ds/dx| = 2 acosh(x)/sqrt(x^2-1)).  Pairs with s~ - Delta >= target are counted, pairs with
+//      s~ + Delta < target are dropped, the (rare) rest goes to a list that recheck_kernel re-scores with
+//      the canonical exact chain (exact_pair) — so counts are identical to CHK_RANK_FMA.  Pairs that are
+//      provably in the clamp regime (x <= 1+eps, every pair at init_size=1e-3) are decided exactly in the
+//      epilogue: their exact score is (bh+bt) + s(1+eps), bit-for-bit what the exact tier computes.
+//
+// Persistent kernel: one CTA per SM, static round-robin over entity tiles, all query tiles per entity
+// tile back-to-back (the entity blocks are re-read from L2, from HBM only once per call).
+#include <cuda_bf16.h>
+#include <cstdio>
+#include <cstdlib>
 #include "chk_common.cuh"
+
+namespace {
+
+constexpr int TILE_E = 128;                 // entity rows per tile  (UMMA M)
+constexpr int TILE_QR = 256;                // query rows per tile   (UMMA N) = 2 rows per query
+constexpr int TILE_Q = TILE_QR / 2;         // queries per tile
+constexpr int KC = 32;                      // K elements per pipeline stage (2 UMMA K-steps of 16)
+constexpr int STAGES = 4;
+constexpr int A_PART = TILE_E * KC * 2;     // bytes of the hi (or lo) half of an entity block
+constexpr int A_BLOCK = 2 * A_PART;         // 16 KB
+constexpr int B_PART = TILE_QR * KC * 2;
+constexpr int B_BLOCK = 2 * B_PART;         // 32 KB
+constexpr int STAGE_BYTES = A_BLOCK + B_BLOCK;
+constexpr int MAX_B = 1024;                 // queries per launch (8 query tiles)
+constexpr int THREADS = 384;                // warp 0 producer, 1 MMA issuer, 2 TMEM alloc, 3 spare, 4..11 epilogue
+constexpr int EPI_WARPS = 8;
+constexpr int TMEM_COLS = 512;
+constexpr int HDR_BYTES = 256;
+constexpr unsigned SPIN_LIMIT = 1u << 28;   // bounded mbarrier spin: a protocol bug traps instead of hanging the GPU
+
+constexpr int SMEM_QC = MAX_B * 16;
+constexpr int SMEM_CNT = MAX_B * 4;
+constexpr int SMEM_BAR = 256;
+constexpr int SMEM_TOTAL = STAGES * STAGE_BYTES + SMEM_QC + SMEM_CNT + SMEM_BAR;
+
+__host__ __device__ inline int kpad_of(int rank) { return (2 * rank + KC - 1) / KC * KC; }
+
+// byte offset of element (row, k) inside one part of a block with R rows (no-swizzle K-major canonical layout):
+// core matrix = 8 rows x 8 bf16 (128 contiguous bytes); K-adjacent core matrices R*16 bytes apart (LBO),
+// row-group-adjacent ones 128 bytes apart (SBO).
+__host__ __device__ inline int tile_off(int R, int row, int k) {
+    return (k >> 3) * (R * 16) + (row >> 3) * 128 + (row & 7) * 16 + (k & 7) * 2;
+}
+
+// ---------------------------------------------------------------------------------------------- PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    unsigned spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > SPIN_LIMIT) { printf("chk_rank_mma: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+    }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float rsqrt_approx(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// shared-memory matrix descriptor, no swizzle, K-major (cute::UMMA::SmemDescriptor bit layout):
+// [0,14) addr>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout=0 (SWIZZLE_NONE)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+// instruction descriptor kind::f16: D=f32 (bit 4), A=B=bf16 (bits 7,10), K-major both, N>>3 at 17, M>>4 at 24
+__host__ __device__ constexpr uint32_t umma_idesc(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------------- operand builders
+__device__ __forceinline__ void split_bf16(float a, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+    hi = __float2bfloat16_rn(a);
+    lo = __float2bfloat16_rn(a - __bfloat162float(hi));
+}
+
+// entity fp32 [n_rows, 2r] -> blocks[(et*nk + kc)] = { hi part | lo part } + nw[e] = ||w_e|| (rounded up)
+__global__ void __launch_bounds__(256) entity_shadow_kernel(const float* __restrict__ entity, int64_t n_rows, int r, int nk,
+                                                            uint8_t* __restrict__ blocks, float* __restrict__ nw) {
+    __shared__ float sT[TILE_E][KC + 1];
+    __shared__ float sSq[TILE_E][4];
+    const int64_t et = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int K2 = 2 * r;
+    float sq[2] = {0.f, 0.f};
+    for (int kc = 0; kc < nk; ++kc) {
+        __syncthreads();
+        for (int idx = tid; idx < TILE_E * KC; idx += 256) {
+            int row = idx / KC, kk = idx - row * KC;
+            int64_t e = et * TILE_E + row;
+            int k = kc * KC + kk;
+            sT[row][kk] = (e < n_rows && k < K2) ? entity[e * K2 + k] : 0.f;
+        }
+        __syncthreads();
+        uint8_t* blk = blocks + ((size_t)et * nk + kc) * A_BLOCK;
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+            int item = tid + it * 256;                 // (row, kcore): consecutive threads -> consecutive rows
+            int row = item & (TILE_E - 1), kcore = item >> 7;
+            __align__(16) __nv_bfloat16 h[8], l[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float a = sT[row][kcore * 8 + j];
+                split_bf16(a, h[j], l[j]);
+                sq[it] = fmaf(a, a, sq[it]);
+            }
+            int off = tile_off(TILE_E, row, kcore * 8);
+            *reinterpret_cast<uint4*>(blk + off) = *reinterpret_cast<const uint4*>(h);
+            *reinterpret_cast<uint4*>(blk + A_PART + off) = *reinterpret_cast<const uint4*>(l);
+        }
+    }
+#pragma unroll
+    for (int it = 0; it < 2; ++it) { int item = tid + it * 256; sSq[item & (TILE_E - 1)][item >> 7] = sq[it]; }
+    __syncthreads();
+    if (tid < TILE_E) {
+        float s = (sSq[tid][0] + sSq[tid][1]) + (sSq[tid][2] + sSq[tid][3]);
+        nw[et * TILE_E + tid] = sqrtf(s) * (1.0f + 1e-6f);
+    }
+}
+
+// q fp32 [b, 2r] -> query blocks[(qt*nk + kc)] (rows 2i: [Re|Im], rows 2i+1: [Im|-Re]); grid (nk, n_qt), 256 threads
+__global__ void __launch_bounds__(256) query_blocks_kernel(const float* __restrict__ q, int b, int r, int nk,
+                                                           uint8_t* __restrict__ blocks) {
+    const int kc = blockIdx.x, qt = blockIdx.y;
+    const int K2 = 2 * r;
+    uint8_t* blk = blocks + ((size_t)qt * nk + kc) * B_BLOCK;
+    for (int item = threadIdx.x; item < TILE_QR * (KC / 8); item += 256) {
+        int row = item & (TILE_QR - 1), kcore = item >> 8;
+        int i = qt * TILE_Q + (row >> 1);
+        bool im_row = row & 1;
+        __align__(16) __nv_bfloat16 h[8], l[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            int k = kc * KC + kcore * 8 + j;
+            float a = 0.f;
+            if (i < b && k < K2) {
+                const float* z = q + (size_t)i * K2;
+                a = !im_row ? z[k] : (k < r ? z[r + k] : -z[k - r]);
+            }
+            split_bf16(a, h[j], l[j]);
+        }
+        int off = tile_off(TILE_QR, row, kcore * 8);
+        *reinterpret_cast<uint4*>(blk + off) = *reinterpret_cast<const uint4*>(h);
+        *reinterpret_cast<uint4*>(blk + B_PART + off) = *reinterpret_cast<const uint4*>(l);
+    }
+}
+
+// per-query constants {2/zn, bh, target, ||z||}; also resets the re-check list counter.  One warp per query.
+__global__ void __launch_bounds__(256) query_consts_kernel(const float* __restrict__ q, const float* __restrict__ qn,
+                                                           const float* __restrict__ bh_vals, const float* __restrict__ target,
+                                                           int b, int r, float4* __restrict__ qc, unsigned* __restrict__ hdr) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) hdr[0] = 0u;
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (i >= b) return;
+    const float* z = q + (size_t)i * 2 * r;
+    float s = 0.f;
+    for (int k = lane; k < 2 * r; k += 32) s = fmaf(z[k], z[k], s);
+    s = warp_sum<float>(s);
+    if (lane == 0) qc[i] = make_float4(2.0f / qn[i], bh_vals ? bh_vals[i] : 0.f, target[i], sqrtf(s) * (1.0f + 1e-6f));
+}
+
+// ---------------------------------------------------------------------------------------------- main kernel
+struct MmaArgs {
+    const uint8_t* a_blocks; const float* nw;          // entity shadow
+    const uint8_t* b_blocks; const float4* qc;         // per-call query operands
+    const float* hn; const float* bt;                  // entity side vectors (bt may be NULL)
+    int64_t n_rows; int b, nk, n_et, n_qt;
+    float eps_dot;                                     // |re~ - re_exact| <= eps_dot * ||z|| ||w|| (both tiers' errors)
+    unsigned* hdr; uint2* list; unsigned list_cap;     // hdr[0] = list length, hdr[1] = overflow flag (sticky)
+    unsigned long long* counts;
+    int dump_raw;                                      // DEBUG bring-up: store (re, im) instead of (score, band)
+    float* dbg_scores; float* dbg_band;                // DEBUG: [b, n_rows] approximate score and band
+};
+
+template <bool DEBUG>
+__global__ void __launch_bounds__(THREADS, 1) rank_mma_kernel(const MmaArgs A) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    float4* sQc = reinterpret_cast<float4*>(smem + STAGES * STAGE_BYTES);
+    int* sCnt = reinterpret_cast<int*>(smem + STAGES * STAGE_BYTES + SMEM_QC);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + SMEM_QC + SMEM_CNT);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + STAGES);
+    const uint32_t bar_tfull = smem_u32(bars + 2 * STAGES), bar_tempty = smem_u32(bars + 2 * STAGES + 2);
+    const uint32_t stage0 = smem_u32(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < MAX_B; i += THREADS) {
+        sQc[i] = i < A.b ? A.qc[i] : make_float4(-2.f, 0.f, 0.f, 0.f);
+        sCnt[i] = 0;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int n_items_et = (A.n_et - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // entity tiles of this CTA
+    const int n_items = n_items_et * A.n_qt;
+
+    if (warp == 0) {
+        // ===== producer: one elected thread issues the bulk copies =====
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int it = 0; it < n_items; ++it) {
+                const int et = blockIdx.x + (it / A.n_qt) * gridDim.x, qt = it % A.n_qt;
+                const uint8_t* asrc = A.a_blocks + (size_t)et * A.nk * A_BLOCK;
+                const uint8_t* bsrc = A.b_blocks + (size_t)qt * A.nk * B_BLOCK;
+                for (int kc = 0; kc < A.nk; ++kc) {
+                    mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                    mbar_arrive_expect_tx(bar_full + 8 * stage, STAGE_BYTES);
+                    const uint32_t dst = stage0 + stage * STAGE_BYTES;
+                    bulk_g2s(dst, asrc + (size_t)kc * A_BLOCK, A_BLOCK, bar_full + 8 * stage);
+                    bulk_g2s(dst + A_BLOCK, bsrc + (size_t)kc * B_BLOCK, B_BLOCK, bar_full + 8 * stage);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: one elected thread =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc(TILE_E, TILE_QR);
+            int stage = 0; uint32_t phase = 0;
+            for (int it = 0; it < n_items; ++it) {
+                const int acc = it & 1; const uint32_t acc_phase = (it >> 1) & 1;
+                mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * TILE_QR;
+                for (int kc = 0; kc < A.nk; ++kc) {
+                    mbar_wait(bar_full + 8 * stage, phase);
+                    tc_fence_after();
+                    const uint32_t sa = stage0 + stage * STAGE_BYTES, sb = sa + A_BLOCK;
+                    constexpr uint32_t a_lbo = TILE_E * 16, a_sbo = 128, b_lbo = TILE_QR * 16, b_sbo = 128;   // K-step / row-group strides
+#pragma unroll
+                    for (int j = 0; j < KC / 16; ++j) {
+                        const uint64_t a_hi = umma_desc(sa + j * (TILE_E * 32), a_lbo, a_sbo);
+                        const uint64_t a_lo = umma_desc(sa + A_PART + j * (TILE_E * 32), a_lbo, a_sbo);
+                        const uint64_t b_hi = umma_desc(sb + j * (TILE_QR * 32), b_lbo, b_sbo);
+                        const uint64_t b_lo = umma_desc(sb + B_PART + j * (TILE_QR * 32), b_lbo, b_sbo);
+                        tc_mma_bf16(d_tmem, a_hi, b_hi, idesc, (kc | j) != 0);
+                        tc_mma_bf16(d_tmem, a_hi, b_lo, idesc, 1);
+                        tc_mma_bf16(d_tmem, a_lo, b_hi, idesc, 1);
+                    }
+                    tc_commit(bar_empty + 8 * stage);            // frees the smem stage when these MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(bar_tfull + 8 * acc);                  // accumulator tile complete
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: TMEM -> registers -> approximate score + band -> counts / re-check list =====
+        const int lq = warp & 3;                       // TMEM lane quarter this warp may read
+        const int chalf = (warp - 4) >> 2;             // which 128 columns (64 queries) of the tile
+        const float xclamp = 1.0f + Sc<float>::ball_eps;
+        const float s_clamp = score_from_x<float>(xclamp, false, 0.f, 0.f);     // exact tier's -acosh(1+eps)^2
+        const float eps = A.eps_dot;
+        const float ca = 1.4142136f * eps, cb = 6.f * eps * eps;
+        constexpr float kx = 16.f * 5.9604645e-8f;                              // roundoff of (x+1) in both tiers
+        constexpr float ks1 = 3.8146973e-6f, ks2 = 9.5367432e-7f, ks3 = 2.3841858e-7f;   // 2^-18, 2^-20, 2^-22
+        for (int it = 0; it < n_items; ++it) {
+            const int et = blockIdx.x + (it / A.n_qt) * gridDim.x, qt = it % A.n_qt;
+            const int acc = it & 1; const uint32_t acc_phase = (it >> 1) & 1;
+            const int64_t e = (int64_t)et * TILE_E + lq * 32 + lane;
+            const bool e_ok = e < A.n_rows;
+            const float iwn = e_ok ? 1.0f / A.hn[e] : -1.0f;
+            const float bte = (e_ok && A.bt) ? A.bt[e] : 0.f;
+            const float nwe = e_ok ? A.nw[e] : 0.f;
+            mbar_wait(bar_tfull + 8 * acc, acc_phase);
+            tc_fence_after();
+            int c0 = 0, c1 = 0;
+#pragma unroll 1
+            for (int g = 0; g < 4; ++g) {
+                uint32_t v[32];
+                tc_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + acc * TILE_QR + chalf * 128 + g * 32, v);
+                tc_wait_ld();
+                if (g == 3) {                          // all TMEM reads of this tile are done: hand the buffer back
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+                }
+                unsigned ambmask = 0;
+                const int qbase = qt * TILE_Q + chalf * 64 + g * 16;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int qi = qbase + j;
+                    const float4 c = sQc[qi];                     // {2/zn, bh, target, ||z||}: warp-uniform broadcast
+                    const float re = __uint_as_float(v[2 * j]), im = __uint_as_float(v[2 * j + 1]);
+                    const float P = c.w * nwe;                    // ||z|| ||w||: delta = eps * P bounds the error of re and im
+                    const float gq = c.x * iwn;                   // 2/(zn wn) > 0
+                    const float r1 = re - 1.0f;
+                    const float mod2 = fmaf(r1, r1, im * im);
+                    // |mod2~ - mod2| <= 2 sqrt2 delta |zw| + 2 delta^2, |zw| <= sqrt(mod2~) + sqrt2 delta, sqrt(m) <= (1+m)/2
+                    const float dm = P * fmaf(cb, P, ca * (1.0f + mod2));
+                    const float xp1 = gq * mod2;
+                    const float x = xp1 - 1.0f;
+                    const float dx = fmaf(gq, dm, xp1 * kx);      // bound on |x~ - x_exact| (before the clamp)
+                    const bool clamped = (x + dx) <= xclamp;      // exact tier's x is clamped for sure
+                    const float xc = fmaxf(x, xclamp);
+                    const float xm = xc - 1.0f;
+                    const float t = xm * (xc + 1.0f);
+                    const float rs = rsqrt_approx(t);
+                    const float sq = t * rs;
+                    const float d = 0.69314718f * lg2_approx(1.0f + (xm + sq));
+                    const float rho = d * rs;                     // acosh(x)/sqrt(x^2-1) = |ds/dx| / 2
+                    const float bias = __fadd_rn(c.y, bte);
+                    const float d2 = d * d;
+                    float s = bias - d2;
+                    float band = fmaf(2.0f * (rho + dx), dx, fmaf(ks1, d2, fmaf(ks2, d, ks3 * fabsf(bias))));
+                    if (clamped) { s = __fadd_rn(bias, s_clamp); band = 0.f; }
+                    const bool live = e_ok && qi < A.b;
+                    const bool sure = live && (s - band >= c.z);
+                    const bool amb = live && !sure && !(s + band < c.z);      // NaN -> re-check
+                    const unsigned m = __ballot_sync(CHK_FULL, sure);
+                    if (lane == ((g * 16 + j) & 31)) { if (g < 2) c0 += __popc(m); else c1 += __popc(m); }
+                    ambmask |= amb ? (1u << j) : 0u;
+                    if (DEBUG) {
+                        if (live) {
+                            A.dbg_scores[(size_t)qi * A.n_rows + e] = A.dump_raw ? re : s;
+                            A.dbg_band[(size_t)qi * A.n_rows + e] = A.dump_raw ? im : band;
+                        }
+                    }
+                }
+                if (__any_sync(CHK_FULL, ambmask != 0)) {
+                    while (ambmask) {
+                        const int j = __ffs(ambmask) - 1;
+                        ambmask &= ambmask - 1;
+                        const unsigned slot = atomicAdd(A.hdr, 1u);
+                        if (slot < A.list_cap) A.list[slot] = make_uint2((unsigned)(qbase + j), (unsigned)e);
+                        else atomicExch(A.hdr + 1, 1u);
+                    }
+                }
+            }
+            // lane l owns queries (chalf*64 + l) and (chalf*64 + 32 + l) of this query tile
+            const int q0 = qt * TILE_Q + chalf * 64 + lane;
+            if (c0) atomicAdd(&sCnt[q0], c0);
+            if (c1) atomicAdd(&sCnt[q0 + 32], c1);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    for (int i = threadIdx.x; i < A.b; i += THREADS)
+        if (sCnt[i]) atomicAdd(A.counts + i, (unsigned long long)sCnt[i]);
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// exact re-check of the pairs the epilogue could not decide (canonical chain -> same bits as the exact tier)
+__global__ void __launch_bounds__(128) recheck_kernel(RArgs<float> A, const unsigned* __restrict__ hdr,
+                                                      const uint2* __restrict__ list, unsigned cap) {
+    const unsigned n = hdr[0] < cap ? hdr[0] : cap;
+    const bool has_bias = A.bt != nullptr;
+    for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+        const uint2 p = list[t];
+        const int64_t i = p.x, e = p.y;
+        float s = exact_pair<float>(A.q + i * 2 * A.r, A.entity + e * 2 * A.r, A.r, A.qn[i], A.hn[e], has_bias,
+                                    has_bias ? A.bh_vals[i] : 0.f, has_bias ? A.bt[e] : 0.f);
+        if (s >= A.target[i]) atomicAdd(A.counts + i, 1ull);
+    }
+}
+
+struct Workspace {
+    unsigned* hdr; float4* qc; uint8_t* b_blocks; uint2* list; unsigned list_cap;
+};
+
+bool carve_workspace(int rank, void* ws, int64_t bytes, Workspace& W) {
+    const int nk = kpad_of(rank) / KC;
+    const int64_t fixed = HDR_BYTES + SMEM_QC + (int64_t)(MAX_B / TILE_Q) * nk * B_BLOCK;
+    if (bytes < fixed + 8 * 1024) return false;
+    uint8_t* p = (uint8_t*)ws;
+    W.hdr = (unsigned*)p;
+    W.qc = (float4*)(p + HDR_BYTES);
+    W.b_blocks = p + HDR_BYTES + SMEM_QC;
+    W.list = (uint2*)(p + fixed);
+    int64_t cap = (bytes - fixed) / 8;
+    W.list_cap = (unsigned)(cap > 0x7fffffff ? 0x7fffffff : cap);
+    return true;
+}
+
+int g_num_sms = 0;
+
+}  // namespace
+
+extern "C" int64_t chk_entity_shadow_bytes(int rank, int64_t n_rows) {
+    if (rank < 2 || n_rows <= 0) return 0;
+    const int64_t n_et = (n_rows + TILE_E - 1) / TILE_E;
+    return n_et * (kpad_of(rank) / KC) * (int64_t)A_BLOCK + n_et * TILE_E * 4;
+}
+
+extern "C" int chk_entity_shadow_build(int rank, int64_t n_rows, const void* entity_f32, void* shadow, void* stream) {
+    if (n_rows == 0) return CHK_OK;
+    if (rank < 2 || n_rows < 0 || !entity_f32 || !shadow) { chk_set_error("chk_entity_shadow_build: bad argument"); return CHK_EINVAL; }
+    const int64_t n_et = (n_rows + TILE_E - 1) / TILE_E;
+    if (n_et > 0x7fffffff) { chk_set_error("chk_entity_shadow_build: shard too large"); return CHK_EUNSUPPORTED; }
+    const int nk = kpad_of(rank) / KC;
+    uint8_t* blocks = (uint8_t*)shadow;
+    float* nw = (float*)(blocks + n_et * nk * (int64_t)A_BLOCK);
+    entity_shadow_kernel<<<(unsigned)n_et, 256, 0, (cudaStream_t)stream>>>((const float*)entity_f32, n_rows, rank, nk, blocks, nw);
+    CHK_CUDA_LAUNCH_CHECK("entity_shadow_kernel");
+    return CHK_OK;
+}
+
+extern "C" int64_t chk_rank_mma_workspace_bytes(int rank, int64_t b) {
+    if (rank < 2) return 0;
+    const int nk = kpad_of(rank) / KC;
+    const int64_t fixed = HDR_BYTES + SMEM_QC + (int64_t)(MAX_B / TILE_Q) * nk * B_BLOCK;
+    int64_t cap = b * 8192;                      // re-check list entries
+    if (cap < (1 << 20)) cap = 1 << 20;
+    if (cap > (8 << 20)) cap = 8 << 20;
+    return fixed + cap * 8;
+}
+
+extern "C" int chk_rank_mma_reset(void* workspace, void* stream) {
+    if (!workspace) { chk_set_error("chk_rank_mma_reset: null workspace"); return CHK_EINVAL; }
+    if (cudaMemsetAsync(workspace, 0, HDR_BYTES, (cudaStream_t)stream) != cudaSuccess) { chk_set_error("cudaMemsetAsync failed"); return CHK_ECUDA; }
+    return CHK_OK;
+}
+
+extern "C" int chk_rank_mma_status(const void* workspace, int64_t* last_list_len, int* overflowed, void* stream) {
+    if (!workspace) { chk_set_error("chk_rank_mma_status: null workspace"); return CHK_EINVAL; }
+    unsigned h[2] = {0, 0};
+    cudaError_t e = cudaMemcpyAsync(h, workspace, sizeof(h), cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
+    if (e != cudaSuccess) { chk_set_error("chk_rank_mma_status: %s", cudaGetErrorString(e)); return CHK_ECUDA; }
+    if (last_list_len) *last_list_len = h[0];
+    if (overflowed) *overflowed = (int)h[1];
+    return CHK_OK;
+}
+
+static int rank_mma_launch(int rank, int64_t b, const void* q, const void* qn, const void* bh_vals, const void* target,
+                           const void* entity, const void* hn, const void* bt, int64_t n_rows, const void* shadow,
+                           void* workspace, int64_t workspace_bytes, int64_t* counts, float* dbg_scores, float* dbg_band,
+                           cudaStream_t st) {
+    Workspace W;
+    if (!carve_workspace(rank, workspace, workspace_bytes, W)) { chk_set_error("CHK_RANK_MMA: workspace too small (%lld bytes)", (long long)workspace_bytes); return CHK_EINVAL; }
+    if (n_rows > 0xffffffffLL) { chk_set_error("CHK_RANK_MMA: shard too large"); return CHK_EUNSUPPORTED; }
+    if (g_num_sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || g_num_sms <= 0) {
+            g_num_sms = 0; chk_set_error("CHK_RANK_MMA: no CUDA device"); return CHK_ECUDA;
+        }
+        if (cudaFuncSetAttribute(rank_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL) != cudaSuccess ||
+            cudaFuncSetAttribute(rank_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL) != cudaSuccess) {
+            g_num_sms = 0; chk_set_error("CHK_RANK_MMA: cannot reserve %d bytes of shared memory: %s", SMEM_TOTAL, cudaGetErrorString(cudaGetLastError())); return CHK_ECUDA;
+        }
+    }
+    const int nk = kpad_of(rank) / KC;
+    const int64_t n_et = (n_rows + TILE_E - 1) / TILE_E;
+    const uint8_t* a_blocks = (const uint8_t*)shadow;
+    const float* nw = (const float*)(a_blocks + n_et * nk * (int64_t)A_BLOCK);
+    // Bound on |re~ - re_exact| (and im) relative to ||z|| ||w|| >= sum_k |z_k||w_k| (Cauchy-Schwarz):
+    //   exact tier's canonical chain: 2r fused steps, each <= 2^-24 relative (standard recursive-summation bound);
+    //   bf16 split: |a - hi - lo| <= 2^-18 |a| per operand plus the dropped lo*lo term -> 3 * 2^-18, rounded up to 2^-16;
+    //   tensor-core accumulation (hardware model, stated in DESIGN.md): every tcgen05.mma K=16 step adds its 16
+    //   exact products to the fp32 accumulator with at most 2 units of 2^-23 relative to the largest magnitude
+    //   involved (<= sum_k |a_k b_k|); 3 * Kpad/16 steps per accumulator.
+    // tests/test_gpu_mma.py checks the observed |s~ - s| against the resulting band (it uses < 5 % of it).
+    const double eps_dot = (2.0 * rank) * 5.9604644775390625e-8 + 1.52587890625e-5 +
+                           2.0 * (3.0 * nk * KC / 16.0) * 1.1920928955078125e-7;
+    for (int64_t b0 = 0; b0 < b; b0 += MAX_B) {
+        const int bc = (int)((b - b0) < MAX_B ? (b - b0) : MAX_B);
+        const int n_qt = (bc + TILE_Q - 1) / TILE_Q;
+        const float* qp = (const float*)q + b0 * 2 * rank;
+        const float* qnp = (const float*)qn + b0;
+        const float* bhp = bh_vals ? (const float*)bh_vals + b0 : nullptr;
+        const float* tp = (const float*)target + b0;
+        query_consts_kernel<<<(bc + 7) / 8, 256, 0, st>>>(qp, qnp, bhp, tp, bc, rank, W.qc, W.hdr);
+        CHK_CUDA_LAUNCH_CHECK("query_consts_kernel");
+        query_blocks_kernel<<<dim3(nk, n_qt), 256, 0, st>>>(qp, bc, rank, nk, W.b_blocks);
+        CHK_CUDA_LAUNCH_CHECK("query_blocks_kernel");
+        MmaArgs A{};
+        A.a_blocks = a_blocks; A.nw = nw; A.b_blocks = W.b_blocks; A.qc = W.qc;
+        A.hn = (const float*)hn; A.bt = (const float*)bt; A.n_rows = n_rows; A.b = bc; A.nk = nk; A.n_et = (int)n_et; A.n_qt = n_qt;
+        A.eps_dot = (float)eps_dot; A.hdr = W.hdr; A.list = W.list; A.list_cap = W.list_cap;
+        A.counts = (unsigned long long*)counts + b0;
+        { const char* dr = getenv("CHK_MMA_DUMP_RAW"); A.dump_raw = (dr && dr[0] == '1') ? 1 : 0; }
+        A.dbg_scores = dbg_scores ? dbg_scores + b0 * n_rows : nullptr;
+        A.dbg_band = dbg_band ? dbg_band + b0 * n_rows : nullptr;
+        const unsigned grid = (unsigned)(n_et < g_num_sms ? n_et : g_num_sms);
+        if (dbg_scores) rank_mma_kernel<true><<<grid, THREADS, SMEM_TOTAL, st>>>(A);
+        else rank_mma_kernel<false><<<grid, THREADS, SMEM_TOTAL, st>>>(A);
+        CHK_CUDA_LAUNCH_CHECK("rank_mma_kernel");
+        RArgs<float> R{};
+        R.q = qp; R.qn = qnp; R.bh_vals = bhp; R.target = tp; R.entity = (const float*)entity; R.hn = (const float*)hn;
+        R.bt = (const float*)bt; R.b = bc; R.n_rows = n_rows; R.r = rank; R.counts = (unsigned long long*)counts + b0;
+        recheck_kernel<<<g_num_sms * 8, 128, 0, st>>>(R, W.hdr, W.list, W.list_cap);
+        CHK_CUDA_LAUNCH_CHECK("recheck_kernel");
+    }
+    return CHK_OK;
+}
 
 int chk_rank_counts_mma(int rank, int64_t b, const void* q, const void* qn, const void* bh_vals,
                         const void* target, const void* entity, const void* hn, const void* bt,
                         int64_t n_rows, const void* shadow, void* workspace, int64_t workspace_bytes,
                         int64_t* counts, cudaStream_t st) {
-    chk_set_error("CHK_RANK_MMA not built yet");
-    return CHK_EUNSUPPORTED;
+    return rank_mma_launch(rank, b, q, qn, bh_vals, target, entity, hn, bt, n_rows, shadow, workspace, workspace_bytes,
+                           counts, nullptr, nullptr, st);
 }
-extern "C" int64_t chk_entity_shadow_bytes(int rank, int64_t n_rows) { return 0; }
-extern "C" int chk_entity_shadow_build(int rank, int64_t n_rows, const void* entity_f32, void* shadow, void* stream) {
-    chk_set_error("CHK_RANK_MMA not built yet");
-    return CHK_EUNSUPPORTED;
+
+extern "C" int chk_score_all_mma(int rank, int64_t b, const void* q, const void* qn, const void* bh_vals,
+                                 const void* target, const void* entity, const void* hn, const void* bt, int64_t n_rows,
+                                 const void* shadow, void* workspace, int64_t workspace_bytes, int64_t* counts,
+                                 void* scores, void* band, void* stream) {
+    if (b == 0 || n_rows == 0) return CHK_OK;
+    if (b < 0 || n_rows < 0 || rank < 2 || !q || !qn || !target || !entity || !hn || !shadow || !workspace || !counts || !scores || !band ||
+        ((bh_vals == nullptr) != (bt == nullptr))) { chk_set_error("chk_score_all_mma: bad argument"); return CHK_EINVAL; }
+    return rank_mma_launch(rank, b, q, qn, bh_vals, target, entity, hn, bt, n_rows, shadow, workspace, workspace_bytes,
+                           counts, (float*)scores, (float*)band, (cudaStream_t)stream);
 }
-extern "C" int64_t chk_rank_mma_workspace_bytes(int rank, int64_t b) { return 0; }

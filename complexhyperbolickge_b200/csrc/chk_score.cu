@@ -78,8 +78,8 @@ __global__ void __launch_bounds__(kWarps * 32) score_gather_kernel(SArgs<T> A) {
             const T d = acosh_x<T>(x);
             if (!BWD) {
                 if (lane == 0) {
-                    T s = -(d * d);
-                    A.scores[pair] = A.bt ? (A.bh_vals[b * A.bh_stride_b + j * A.bh_stride_j] + A.bt[row]) + s : s;
+                    T s = -Sc<T>::mul_(d, d);
+                    A.scores[pair] = A.bt ? Sc<T>::add_(Sc<T>::add_(A.bh_vals[b * A.bh_stride_b + j * A.bh_stride_j], A.bt[row]), s) : s;
                 }
             } else {
                 const T gd = T(-2) * d * A.grad_scores[pair];

@@ -154,7 +154,40 @@ def mma_available(rank: int = 257) -> bool:
 
 def rank_mma_workspace(rank, b, device):
     nbytes = _lib.lib().chk_rank_mma_workspace_bytes(rank, b)
-    return torch.zeros((max(nbytes, 16),), dtype=torch.uint8, device=device)
+    if nbytes <= 0:
+        raise RuntimeError("CHK_RANK_MMA workspace unavailable: " + _lib.lib().chk_last_error().decode())
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=device)
+    rank_mma_reset(ws)
+    return ws
+
+
+def rank_mma_reset(workspace):
+    _chk(workspace)
+    _lib.check(_lib.lib().chk_rank_mma_reset(_p(workspace), _stream()), "chk_rank_mma_reset")
+
+
+def rank_mma_status(workspace):
+    """(length of the last re-check list, sticky overflow flag); synchronises the current stream."""
+    import ctypes
+    _chk(workspace)
+    n, ov = ctypes.c_int64(0), ctypes.c_int(0)
+    _lib.check(_lib.lib().chk_rank_mma_status(_p(workspace), ctypes.byref(n), ctypes.byref(ov), _stream()),
+               "chk_rank_mma_status")
+    return n.value, bool(ov.value)
+
+
+def score_all_mma(rank, q, qn, bh_vals, target, entity, hn, bt, shadow, workspace):
+    """Test support: tensor-core tier approximate scores, error bands and (unfiltered) counts."""
+    _chk(q, qn, bh_vals, target, entity, hn, bt, shadow, workspace)
+    b, n = q.shape[0], entity.shape[0]
+    scores = torch.full((b, n), float("nan"), dtype=torch.float32, device=q.device)
+    band = torch.full((b, n), float("nan"), dtype=torch.float32, device=q.device)
+    counts = torch.zeros((b,), dtype=torch.int64, device=q.device)
+    _lib.check(_lib.lib().chk_score_all_mma(rank, b, _p(q), _p(qn), _p(bh_vals), _p(target), _p(entity), _p(hn),
+                                            _p(bt), n, _p(shadow), _p(workspace),
+                                            workspace.numel() * workspace.element_size(), _p(counts), _p(scores),
+                                            _p(band), _stream()), "chk_score_all_mma")
+    return scores, band, counts
 
 
 # ------------------------------------------------------------------------------------------- autograd

@@ -85,6 +85,17 @@ def rank_queries(model, queries: torch.Tensor, findex: FilterIndex, batch_size: 
             ix = torch.from_numpy(idx).to(dev, non_blocking=True) if idx.size else torch.zeros(1, dtype=torch.int64, device=dev)
             target = rank_batch(model, state, qd, ip, ix, int(idx.size), counts_all[b0:b0 + batch_size], ws)
             assert not torch.isnan(target).any()          # models/base.py:259-260
+        if ws is not None and ops.rank_mma_status(ws)[1]:
+            # the re-check list of some batch overflowed (pathological tie mass): redo the pass on the exact tier
+            state.algo, state.shadow = ops.CHK_RANK_FMA, None
+            counts_all.zero_()
+            for b0 in range(0, n, batch_size):
+                qb = q_np[b0:b0 + batch_size]
+                indptr, idx = findex.batch_csr(qb)
+                qd = torch.from_numpy(np.ascontiguousarray(qb)).to(dev)
+                ix = torch.from_numpy(idx).to(dev) if idx.size else torch.zeros(1, dtype=torch.int64, device=dev)
+                rank_batch(model, state, qd, torch.from_numpy(indptr).to(dev), ix, int(idx.size),
+                           counts_all[b0:b0 + batch_size], None)
         if state.world > 1:
             import torch.distributed as dist
             dist.all_reduce(counts_all, op=dist.ReduceOp.SUM, group=model.process_group)

@@ -109,10 +109,13 @@ int chk_target_scores(int dtype, int rank, int64_t b, const void* q, const void*
  * filter_indptr[b].  Shard rows are global ids [shard_offset, shard_offset + n_rows).  counts is int64 [b],
  * accumulated (caller zeroes it); summing it over shards / GPUs gives rank - 1.
  * algo = CHK_RANK_FMA: exact fp32/fp64 FMA tiles.
- * algo = CHK_RANK_MMA (fp32 only): tcgen05 bf16x3 tiles decide every pair whose score is outside a proven
- *   error band around the target and the pairs inside the band are re-scored with the exact chain, so the
- *   counts equal CHK_RANK_FMA's; needs the shadow from chk_entity_shadow_build and a workspace of
- *   chk_rank_mma_workspace_bytes(rank, b) bytes (returns CHK_EOVERFLOW if the band list overflows). */
+ * algo = CHK_RANK_MMA (fp32 only): the contraction runs on tcgen05 (bf16x3 split, fp32 accumulation in TMEM) from
+ *   the pre-tiled bf16 shadow of chk_entity_shadow_build; the epilogue decides every pair whose approximate
+ *   score is outside a proven error band around the target, and the pairs inside the band are re-scored with
+ *   the exact chain, so the counts EQUAL CHK_RANK_FMA's.  Needs `shadow` (built for the same entity/n_rows) and
+ *   a workspace of chk_rank_mma_workspace_bytes(rank, b) bytes.  If the band list overflows, a sticky flag is
+ *   raised in the workspace (read it with chk_rank_mma_status after the pass; the counts of that pass are then
+ *   invalid and the caller re-runs it with CHK_RANK_FMA). */
 int chk_rank_counts(int algo, int dtype, int rank, int64_t b, const void* q, const void* qn,
                     const void* bh_vals, const void* target, const void* entity, const void* hn,
                     const void* bt, int64_t n_rows, int64_t shard_offset,
@@ -122,6 +125,16 @@ int chk_rank_counts(int algo, int dtype, int rank, int64_t b, const void* q, con
 int64_t chk_entity_shadow_bytes(int rank, int64_t n_rows);
 int chk_entity_shadow_build(int rank, int64_t n_rows, const void* entity_f32, void* shadow, void* stream);
 int64_t chk_rank_mma_workspace_bytes(int rank, int64_t b);
+/* Zero the workspace header (list length + sticky overflow flag); call once before a ranking pass. */
+int chk_rank_mma_reset(void* workspace, void* stream);
+/* Synchronises `stream` and reads the header back: length of the last re-check list, sticky overflow flag. */
+int chk_rank_mma_status(const void* workspace, int64_t* last_list_len, int* overflowed, void* stream);
+/* Test support (like chk_score_all): the tensor-core tier's approximate scores [b,n_rows] and error bands
+ * [b,n_rows] (band 0 = decided exactly in the clamp regime), plus its counts (no filter pass). */
+int chk_score_all_mma(int rank, int64_t b, const void* q, const void* qn, const void* bh_vals,
+                      const void* target, const void* entity, const void* hn, const void* bt, int64_t n_rows,
+                      const void* shadow, void* workspace, int64_t workspace_bytes, int64_t* counts,
+                      void* scores, void* band, void* stream);
 
 #ifdef __cplusplus
 }
