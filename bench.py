@@ -263,7 +263,7 @@ def run_ours(args):
         steps_in.append((torch.from_numpy(qb).to(device), torch.from_numpy(indptr).to(device),
                          torch.from_numpy(idx).to(device), int(idx.size)))
     with torch.no_grad():
-        state = ranking.EvalState(model)
+        state = ranking.eval_state(model)
         ws = ops.rank_mma_workspace(rank, b, device) if state.algo == ops.CHK_RANK_MMA else None
         counts = torch.zeros(b, dtype=torch.int64, device=device)
 

@@ -139,3 +139,38 @@ template <typename T> struct RArgs {
     T* scores;                       // MODE 0: [b, n_rows]
     unsigned long long* counts;      // MODE 1: [b]
 };
+
+// ---- exact per-pair scores, one LANE per pair, rows staged by the whole warp --------------------------
+// Same arithmetic and order as exact_pair() (each lane walks k = 0..r-1 of its own pair), but the 2r-wide
+// rows are fetched with coalesced 128-byte warp loads, 32 complex coefficients at a time, through a padded
+// shared-memory transpose.  Used wherever a list of scattered (query, entity) pairs must be scored exactly:
+// the filter pass and the re-check of the tensor-core tier.
+template <typename T> struct PairTiles { T zr[32][33], zi[32][33], wr[32][33], wi[32][33]; };
+
+template <typename T>
+__device__ __forceinline__ T warp_exact_pairs(const RArgs<T>& A, unsigned i, unsigned e, bool valid, PairTiles<T>& S) {
+    const int lane = threadIdx.x & 31;
+    const int r = A.r;
+    T re = T(0), im = T(0);
+    for (int k0 = 0; k0 < r; k0 += 32) {
+        const int kc = min(32, r - k0);
+        __syncwarp();
+#pragma unroll 4
+        for (int p = 0; p < 32; ++p) {
+            const unsigned ip = __shfl_sync(CHK_FULL, i, p), ep = __shfl_sync(CHK_FULL, e, p);
+            const int vp = __shfl_sync(CHK_FULL, (int)valid, p);
+            if (vp && lane < kc) {
+                const T* z = A.q + (size_t)ip * 2 * r + k0 + lane;
+                const T* w = A.entity + (size_t)ep * 2 * r + k0 + lane;
+                S.zr[p][lane] = z[0]; S.zi[p][lane] = z[r];
+                S.wr[p][lane] = w[0]; S.wi[p][lane] = w[r];
+            }
+        }
+        __syncwarp();
+        if (valid)
+            for (int kk = 0; kk < kc; ++kk) dot_step<T>(S.zr[lane][kk], S.zi[lane][kk], S.wr[lane][kk], S.wi[lane][kk], re, im);
+    }
+    if (!valid) return T(0);
+    const bool has_bias = A.bt != nullptr;
+    return pair_score<T>(re, im, A.qn[i], A.hn[e], has_bias, has_bias ? A.bh_vals[i] : T(0), has_bias ? A.bt[e] : T(0));
+}

@@ -156,21 +156,27 @@ __global__ void target_kernel(const T* q, const T* qn, const T* bh_vals, const T
                               has_bias ? bh_vals[i] : T(0), has_bias ? tail_bt[i] : T(0));
 }
 
-// counts[i] -= #{ e in filter_i within the shard : score(i,e) >= target[i] }; one thread per filter entry.
+// counts[i] -= #{ e in filter_i within the shard : score(i,e) >= target[i] }; one lane per filter entry, rows
+// staged by the warp (warp_exact_pairs).
 template <typename T>
-__global__ void filter_sub_kernel(RArgs<T> A, const int64_t* __restrict__ indptr, const int64_t* __restrict__ fidx,
-                                  int64_t shard_offset, int64_t total) {
-    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-        // binary search the owning query: largest i with indptr[i] <= t
-        int64_t lo = 0, hi = A.b;
-        while (hi - lo > 1) { int64_t mid = (lo + hi) >> 1; if (indptr[mid] <= t) lo = mid; else hi = mid; }
-        const int64_t i = lo;
-        const int64_t e = fidx[t] - shard_offset;
-        if (e < 0 || e >= A.n_rows) continue;
-        bool has_bias = A.bt != nullptr;
-        T s = exact_pair<T>(A.q + i * 2 * A.r, A.entity + e * 2 * A.r, A.r, A.qn[i], A.hn[e], has_bias,
-                            has_bias ? A.bh_vals[i] : T(0), has_bias ? A.bt[e] : T(0));
-        if (s >= A.target[i]) atomicAdd(A.counts + i, (unsigned long long)(-1LL));
+__global__ void __launch_bounds__(32) filter_sub_kernel(RArgs<T> A, const int64_t* __restrict__ indptr,
+                                                        const int64_t* __restrict__ fidx, int64_t shard_offset, int64_t total) {
+    __shared__ PairTiles<T> S;
+    for (int64_t t0 = (int64_t)blockIdx.x * 32; t0 < total; t0 += (int64_t)gridDim.x * 32) {
+        const int64_t t = t0 + threadIdx.x;
+        bool valid = t < total;
+        int64_t i = 0, e = 0;
+        if (valid) {
+            // binary search the owning query: largest i with indptr[i] <= t
+            int64_t lo = 0, hi = A.b;
+            while (hi - lo > 1) { int64_t mid = (lo + hi) >> 1; if (indptr[mid] <= t) lo = mid; else hi = mid; }
+            i = lo;
+            e = fidx[t] - shard_offset;
+            valid = e >= 0 && e < A.n_rows;
+        }
+        if (!__any_sync(CHK_FULL, valid)) continue;
+        const T s = warp_exact_pairs<T>(A, (unsigned)i, (unsigned)e, valid, S);
+        if (valid && s >= A.target[i]) atomicAdd(A.counts + i, (unsigned long long)(-1LL));
     }
 }
 
@@ -269,10 +275,10 @@ int chk_filter_subtract(int dtype, int rank, int64_t b, const void* q, const voi
                         int64_t n_rows, int64_t shard_offset, const int64_t* indptr, const int64_t* fidx,
                         int64_t total, int64_t* counts, cudaStream_t st) {
     if (total <= 0) return CHK_OK;
-    int64_t blocks = (total + 127) / 128;
-    if (blocks > 148 * 64) blocks = 148 * 64;
-    if (dtype == CHK_F32) { auto A = make_rargs<float>(rank, b, q, qn, bh_vals, target, entity, hn, bt, n_rows); A.counts = (unsigned long long*)counts; filter_sub_kernel<float><<<(unsigned)blocks, 128, 0, st>>>(A, indptr, fidx, shard_offset, total); }
-    else if (dtype == CHK_F64) { auto A = make_rargs<double>(rank, b, q, qn, bh_vals, target, entity, hn, bt, n_rows); A.counts = (unsigned long long*)counts; filter_sub_kernel<double><<<(unsigned)blocks, 128, 0, st>>>(A, indptr, fidx, shard_offset, total); }
+    int64_t blocks = (total + 31) / 32;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    if (dtype == CHK_F32) { auto A = make_rargs<float>(rank, b, q, qn, bh_vals, target, entity, hn, bt, n_rows); A.counts = (unsigned long long*)counts; filter_sub_kernel<float><<<(unsigned)blocks, 32, 0, st>>>(A, indptr, fidx, shard_offset, total); }
+    else if (dtype == CHK_F64) { auto A = make_rargs<double>(rank, b, q, qn, bh_vals, target, entity, hn, bt, n_rows); A.counts = (unsigned long long*)counts; filter_sub_kernel<double><<<(unsigned)blocks, 32, 0, st>>>(A, indptr, fidx, shard_offset, total); }
     else { chk_set_error("unknown dtype %d", dtype); return CHK_EINVAL; }
     CHK_CUDA_LAUNCH_CHECK("filter_sub_kernel");
     return CHK_OK;

@@ -39,12 +39,10 @@ constexpr int TILE_E = 128;                 // entity rows per tile  (UMMA M)
 constexpr int TILE_QR = 256;                // query rows per tile   (UMMA N) = 2 rows per query
 constexpr int TILE_Q = TILE_QR / 2;         // queries per tile
 constexpr int KC = 32;                      // K elements per pipeline stage (2 UMMA K-steps of 16)
-constexpr int STAGES = 4;
 constexpr int A_PART = TILE_E * KC * 2;     // bytes of the hi (or lo) half of an entity block
 constexpr int A_BLOCK = 2 * A_PART;         // 16 KB
 constexpr int B_PART = TILE_QR * KC * 2;
 constexpr int B_BLOCK = 2 * B_PART;         // 32 KB
-constexpr int STAGE_BYTES = A_BLOCK + B_BLOCK;
 constexpr int MAX_B = 1024;                 // queries per launch (8 query tiles)
 constexpr int THREADS = 384;                // warp 0 producer, 1 MMA issuer, 2 TMEM alloc, 3 spare, 4..11 epilogue
 constexpr int EPI_WARPS = 8;
@@ -55,7 +53,6 @@ constexpr unsigned SPIN_LIMIT = 1u << 28;   // bounded mbarrier spin: a protocol
 constexpr int SMEM_QC = MAX_B * 16;
 constexpr int SMEM_CNT = MAX_B * 4;
 constexpr int SMEM_BAR = 256;
-constexpr int SMEM_TOTAL = STAGES * STAGE_BYTES + SMEM_QC + SMEM_CNT + SMEM_BAR;
 
 __host__ __device__ inline int kpad_of(int rank) { return (2 * rank + KC - 1) / KC * KC; }
 
@@ -185,7 +182,8 @@ __global__ void __launch_bounds__(256) entity_shadow_kernel(const float* __restr
 }
 
 // q fp32 [b, 2r] -> query blocks[(qt*nk + kc)] (rows 2i: [Re|Im], rows 2i+1: [Im|-Re]); grid (nk, n_qt), 256 threads
-__global__ void __launch_bounds__(256) query_blocks_kernel(const float* __restrict__ q, int b, int r, int nk,
+// pair_layout: the block is two 128-row halves {hi | lo}{hi | lo} (one per CTA of a pair) instead of {hi | lo} of 256 rows
+__global__ void __launch_bounds__(256) query_blocks_kernel(const float* __restrict__ q, int b, int r, int nk, int pair_layout,
                                                            uint8_t* __restrict__ blocks) {
     const int kc = blockIdx.x, qt = blockIdx.y;
     const int K2 = 2 * r;
@@ -205,9 +203,11 @@ __global__ void __launch_bounds__(256) query_blocks_kernel(const float* __restri
             }
             split_bf16(a, h[j], l[j]);
         }
-        int off = tile_off(TILE_QR, row, kcore * 8);
+        int off, lo_off;
+        if (pair_layout) { off = (row >> 7) * (B_BLOCK / 2) + tile_off(TILE_QR / 2, row & 127, kcore * 8); lo_off = B_PART / 2; }
+        else { off = tile_off(TILE_QR, row, kcore * 8); lo_off = B_PART; }
         *reinterpret_cast<uint4*>(blk + off) = *reinterpret_cast<const uint4*>(h);
-        *reinterpret_cast<uint4*>(blk + B_PART + off) = *reinterpret_cast<const uint4*>(l);
+        *reinterpret_cast<uint4*>(blk + lo_off + off) = *reinterpret_cast<const uint4*>(l);
     }
 }
 
@@ -239,26 +239,104 @@ struct MmaArgs {
     float* dbg_scores; float* dbg_band;                // DEBUG: [b, n_rows] approximate score and band
 };
 
-template <bool DEBUG>
+// Geometry of the two variants.
+//   PAIR = false: one CTA per tile, tcgen05.mma.cta_group::1, M = 128 entities x N = 256 query rows; per stage the
+//                 CTA stages its entity block and the WHOLE query block (48 KB at KC = 32).
+//   PAIR = true : a 2-CTA cluster per tile pair, tcgen05.mma.cta_group::2 issued by the leader CTA, M = 256 entities
+//                 (128 TMEM lanes in each CTA) x N = 256 query rows; each CTA stages its own entity block and HALF
+//                 of the query block (32 KB per stage) — the tensor core reads the other half from the peer's shared
+//                 memory, which halves the query-side shared-memory fill and read traffic per CTA.
+template <bool PAIR> struct Geo {
+    static constexpr int B_ROWS = PAIR ? TILE_QR / 2 : TILE_QR;      // query rows staged per CTA
+    static constexpr int B_BYTES = 2 * B_ROWS * KC * 2;              // hi + lo
+    static constexpr int STAGE = A_BLOCK + B_BYTES;
+    static constexpr int NSTAGE = PAIR ? 6 : 4;
+    static constexpr int NBAR = 3 * NSTAGE + 4;                      // full, empty, peer_full, tfull[2], tempty[2]
+    static constexpr int SMEM = NSTAGE * STAGE + SMEM_QC + SMEM_CNT + SMEM_BAR;
+    static constexpr int UMMA_M = PAIR ? 2 * TILE_E : TILE_E;
+};
+
+template <bool PAIR> __device__ __forceinline__ void tc_mma_issue(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if constexpr (PAIR) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+    } else {
+        tc_mma_bf16(d_tmem, adesc, bdesc, idesc, accumulate);
+    }
+}
+// MMA-completion arrive; PAIR: on the barrier at this offset in BOTH CTAs of the pair
+template <bool PAIR> __device__ __forceinline__ void tc_commit_to(uint32_t bar) {
+    if constexpr (PAIR) {
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                     ::"r"(bar), "h"((uint16_t)3) : "memory");
+    } else {
+        tc_commit(bar);
+    }
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_id_x() { uint32_t r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_nid_x() { uint32_t r; asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at local address `bar` of CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+        ::"r"(bar), "r"(rank) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    unsigned spins = 0;
+    while (!mbar_try_wait_cluster(bar, parity)) {
+        if (++spins > SPIN_LIMIT) { printf("chk_rank_mma: cluster mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+    }
+}
+
+template <bool DEBUG, bool PAIR>
 __global__ void __launch_bounds__(THREADS, 1) rank_mma_kernel(const MmaArgs A) {
+    using G = Geo<PAIR>;
+    constexpr int NS = G::NSTAGE;
     extern __shared__ __align__(1024) uint8_t smem[];
-    float4* sQc = reinterpret_cast<float4*>(smem + STAGES * STAGE_BYTES);
-    int* sCnt = reinterpret_cast<int*>(smem + STAGES * STAGE_BYTES + SMEM_QC);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + SMEM_QC + SMEM_CNT);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-    const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + STAGES);
-    const uint32_t bar_tfull = smem_u32(bars + 2 * STAGES), bar_tempty = smem_u32(bars + 2 * STAGES + 2);
+    float4* sQc = reinterpret_cast<float4*>(smem + NS * G::STAGE);
+    int* sCnt = reinterpret_cast<int*>(smem + NS * G::STAGE + SMEM_QC);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NS * G::STAGE + SMEM_QC + SMEM_CNT);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + G::NBAR);
+    const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + NS), bar_pfull = smem_u32(bars + 2 * NS);
+    const uint32_t bar_tfull = smem_u32(bars + 3 * NS), bar_tempty = smem_u32(bars + 3 * NS + 2);
     const uint32_t stage0 = smem_u32(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t crank = PAIR ? cluster_ctarank() : 0u;              // 0 = leader (issues the MMAs)
+    const int unit = PAIR ? (int)cluster_id_x() : (int)blockIdx.x;     // persistent work unit (CTA or CTA pair)
+    const int n_units = PAIR ? (int)cluster_nid_x() : (int)gridDim.x;
+    const int n_super = PAIR ? (A.n_et + 1) / 2 : A.n_et;              // entity tiles (or tile pairs) in the shard
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, EPI_WARPS); }
+        for (int s = 0; s < NS; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); mbar_init(bar_pfull + 8 * s, 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, PAIR ? 2 * EPI_WARPS : EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if constexpr (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     for (int i = threadIdx.x; i < MAX_B; i += THREADS) {
         sQc[i] = i < A.b ? A.qc[i] : make_float4(-2.f, 0.f, 0.f, 0.f);
@@ -266,59 +344,73 @@ __global__ void __launch_bounds__(THREADS, 1) rank_mma_kernel(const MmaArgs A) {
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();            // both CTAs' barriers and TMEM exist before any cross-CTA signal
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int n_items_et = (A.n_et - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // entity tiles of this CTA
-    const int n_items = n_items_et * A.n_qt;
+    const int n_items = ((n_super - unit + n_units - 1) / n_units) * A.n_qt;
 
     if (warp == 0) {
-        // ===== producer: one elected thread issues the bulk copies =====
+        // ===== producer: one elected thread issues the bulk copies of this CTA's operands =====
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             for (int it = 0; it < n_items; ++it) {
-                const int et = blockIdx.x + (it / A.n_qt) * gridDim.x, qt = it % A.n_qt;
+                const int sup = unit + (it / A.n_qt) * n_units, qt = it % A.n_qt;
+                const int et = PAIR ? 2 * sup + (int)crank : sup;      // the shadow is padded to an even tile count
                 const uint8_t* asrc = A.a_blocks + (size_t)et * A.nk * A_BLOCK;
-                const uint8_t* bsrc = A.b_blocks + (size_t)qt * A.nk * B_BLOCK;
+                const uint8_t* bsrc = A.b_blocks + (size_t)qt * A.nk * B_BLOCK + (PAIR ? crank * G::B_BYTES : 0);
                 for (int kc = 0; kc < A.nk; ++kc) {
-                    mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-                    mbar_arrive_expect_tx(bar_full + 8 * stage, STAGE_BYTES);
-                    const uint32_t dst = stage0 + stage * STAGE_BYTES;
+                    mbar_wait_cluster(bar_empty + 8 * stage, phase ^ 1);
+                    mbar_arrive_expect_tx(bar_full + 8 * stage, G::STAGE);
+                    const uint32_t dst = stage0 + stage * G::STAGE;
                     bulk_g2s(dst, asrc + (size_t)kc * A_BLOCK, A_BLOCK, bar_full + 8 * stage);
-                    bulk_g2s(dst + A_BLOCK, bsrc + (size_t)kc * B_BLOCK, B_BLOCK, bar_full + 8 * stage);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    bulk_g2s(dst + A_BLOCK, bsrc + (size_t)kc * B_BLOCK, G::B_BYTES, bar_full + 8 * stage);
+                    if (++stage == NS) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer: one elected thread =====
         if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc(TILE_E, TILE_QR);
-            int stage = 0; uint32_t phase = 0;
-            for (int it = 0; it < n_items; ++it) {
-                const int acc = it & 1; const uint32_t acc_phase = (it >> 1) & 1;
-                mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * TILE_QR;
-                for (int kc = 0; kc < A.nk; ++kc) {
-                    mbar_wait(bar_full + 8 * stage, phase);
+            if (crank == 0) {
+                // ===== MMA issuer: one elected thread of the leader CTA =====
+                constexpr uint32_t idesc = umma_idesc(G::UMMA_M, TILE_QR);
+                constexpr uint32_t a_lbo = TILE_E * 16, b_lbo = G::B_ROWS * 16, sbo = 128;   // K-step / row-group strides
+                constexpr uint32_t b_part = G::B_ROWS * KC * 2;
+                int stage = 0; uint32_t phase = 0;
+                for (int it = 0; it < n_items; ++it) {
+                    const int acc = it & 1; const uint32_t acc_phase = (it >> 1) & 1;
+                    mbar_wait_cluster(bar_tempty + 8 * acc, acc_phase ^ 1);
                     tc_fence_after();
-                    const uint32_t sa = stage0 + stage * STAGE_BYTES, sb = sa + A_BLOCK;
-                    constexpr uint32_t a_lbo = TILE_E * 16, a_sbo = 128, b_lbo = TILE_QR * 16, b_sbo = 128;   // K-step / row-group strides
+                    const uint32_t d_tmem = tmem_base + acc * TILE_QR;
+                    for (int kc = 0; kc < A.nk; ++kc) {
+                        mbar_wait(bar_full + 8 * stage, phase);
+                        if constexpr (PAIR) mbar_wait_cluster(bar_pfull + 8 * stage, phase);   // the peer's operands landed too
+                        tc_fence_after();
+                        const uint32_t sa = stage0 + stage * G::STAGE, sb = sa + A_BLOCK;
 #pragma unroll
-                    for (int j = 0; j < KC / 16; ++j) {
-                        const uint64_t a_hi = umma_desc(sa + j * (TILE_E * 32), a_lbo, a_sbo);
-                        const uint64_t a_lo = umma_desc(sa + A_PART + j * (TILE_E * 32), a_lbo, a_sbo);
-                        const uint64_t b_hi = umma_desc(sb + j * (TILE_QR * 32), b_lbo, b_sbo);
-                        const uint64_t b_lo = umma_desc(sb + B_PART + j * (TILE_QR * 32), b_lbo, b_sbo);
-                        tc_mma_bf16(d_tmem, a_hi, b_hi, idesc, (kc | j) != 0);
-                        tc_mma_bf16(d_tmem, a_hi, b_lo, idesc, 1);
-                        tc_mma_bf16(d_tmem, a_lo, b_hi, idesc, 1);
+                        for (int j = 0; j < KC / 16; ++j) {
+                            const uint64_t a_hi = umma_desc(sa + j * (TILE_E * 32), a_lbo, sbo);
+                            const uint64_t a_lo = umma_desc(sa + A_PART + j * (TILE_E * 32), a_lbo, sbo);
+                            const uint64_t b_hi = umma_desc(sb + j * (G::B_ROWS * 32), b_lbo, sbo);
+                            const uint64_t b_lo = umma_desc(sb + b_part + j * (G::B_ROWS * 32), b_lbo, sbo);
+                            tc_mma_issue<PAIR>(d_tmem, a_hi, b_hi, idesc, (kc | j) != 0);
+                            tc_mma_issue<PAIR>(d_tmem, a_hi, b_lo, idesc, 1);
+                            tc_mma_issue<PAIR>(d_tmem, a_lo, b_hi, idesc, 1);
+                        }
+                        tc_commit_to<PAIR>(bar_empty + 8 * stage);        // frees the smem stage (in both CTAs) when these MMAs retire
+                        if (++stage == NS) { stage = 0; phase ^= 1; }
                     }
-                    tc_commit(bar_empty + 8 * stage);            // frees the smem stage when these MMAs retire
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    tc_commit_to<PAIR>(bar_tfull + 8 * acc);              // accumulator tile complete (both CTAs' epilogues)
                 }
-                tc_commit(bar_tfull + 8 * acc);                  // accumulator tile complete
+            } else {
+                // ===== peer CTA: relay "my operands have landed" to the leader's peer_full barriers =====
+                int stage = 0; uint32_t phase = 0;
+                for (int it = 0; it < n_items; ++it)
+                    for (int kc = 0; kc < A.nk; ++kc) {
+                        mbar_wait(bar_full + 8 * stage, phase);
+                        mbar_arrive_cluster(bar_pfull + 8 * stage, 0);
+                        if (++stage == NS) { stage = 0; phase ^= 1; }
+                    }
             }
         }
     } else if (warp >= 4) {
@@ -332,14 +424,15 @@ __global__ void __launch_bounds__(THREADS, 1) rank_mma_kernel(const MmaArgs A) {
         constexpr float kx = 16.f * 5.9604645e-8f;                              // roundoff of (x+1) in both tiers
         constexpr float ks1 = 3.8146973e-6f, ks2 = 9.5367432e-7f, ks3 = 2.3841858e-7f;   // 2^-18, 2^-20, 2^-22
         for (int it = 0; it < n_items; ++it) {
-            const int et = blockIdx.x + (it / A.n_qt) * gridDim.x, qt = it % A.n_qt;
+            const int sup = unit + (it / A.n_qt) * n_units, qt = it % A.n_qt;
+            const int et = PAIR ? 2 * sup + (int)crank : sup;
             const int acc = it & 1; const uint32_t acc_phase = (it >> 1) & 1;
             const int64_t e = (int64_t)et * TILE_E + lq * 32 + lane;
             const bool e_ok = e < A.n_rows;
             const float iwn = e_ok ? 1.0f / A.hn[e] : -1.0f;
             const float bte = (e_ok && A.bt) ? A.bt[e] : 0.f;
             const float nwe = e_ok ? A.nw[e] : 0.f;
-            mbar_wait(bar_tfull + 8 * acc, acc_phase);
+            mbar_wait_cluster(bar_tfull + 8 * acc, acc_phase);
             tc_fence_after();
             int c0 = 0, c1 = 0;
 #pragma unroll 1
@@ -350,7 +443,7 @@ __global__ void __launch_bounds__(THREADS, 1) rank_mma_kernel(const MmaArgs A) {
                 if (g == 3) {                          // all TMEM reads of this tile are done: hand the buffer back
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+                    if (lane == 0) { if constexpr (PAIR) mbar_arrive_cluster(bar_tempty + 8 * acc, 0); else mbar_arrive(bar_tempty + 8 * acc); }
                 }
                 unsigned ambmask = 0;
                 const int qbase = qt * TILE_Q + chalf * 64 + g * 16;
@@ -412,25 +505,30 @@ __global__ void __launch_bounds__(THREADS, 1) rank_mma_kernel(const MmaArgs A) {
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();            // no CTA leaves while its peer may still signal it or read its smem
     for (int i = threadIdx.x; i < A.b; i += THREADS)
         if (sCnt[i]) atomicAdd(A.counts + i, (unsigned long long)sCnt[i]);
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+        if constexpr (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
 }
 
-// exact re-check of the pairs the epilogue could not decide (canonical chain -> same bits as the exact tier)
-__global__ void __launch_bounds__(128) recheck_kernel(RArgs<float> A, const unsigned* __restrict__ hdr,
-                                                      const uint2* __restrict__ list, unsigned cap) {
+// exact re-check of the pairs the epilogue could not decide (canonical chain -> same bits as the exact tier);
+// one lane per pair, rows staged with coalesced warp loads (warp_exact_pairs)
+constexpr int RECHECK_WARPS = 2;
+__global__ void __launch_bounds__(RECHECK_WARPS * 32) recheck_kernel(RArgs<float> A, const unsigned* __restrict__ hdr,
+                                                                     const uint2* __restrict__ list, unsigned cap) {
+    __shared__ PairTiles<float> S[RECHECK_WARPS];
     const unsigned n = hdr[0] < cap ? hdr[0] : cap;
-    const bool has_bias = A.bt != nullptr;
-    for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
-        const uint2 p = list[t];
-        const int64_t i = p.x, e = p.y;
-        float s = exact_pair<float>(A.q + i * 2 * A.r, A.entity + e * 2 * A.r, A.r, A.qn[i], A.hn[e], has_bias,
-                                    has_bias ? A.bh_vals[i] : 0.f, has_bias ? A.bt[e] : 0.f);
-        if (s >= A.target[i]) atomicAdd(A.counts + i, 1ull);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (unsigned t0 = (blockIdx.x * RECHECK_WARPS + warp) * 32; t0 < n; t0 += gridDim.x * RECHECK_WARPS * 32) {
+        const unsigned t = t0 + lane;
+        const bool valid = t < n;
+        const uint2 p = valid ? list[t] : make_uint2(0u, 0u);
+        const float s = warp_exact_pairs<float>(A, p.x, p.y, valid, S[warp]);
+        if (valid && s >= A.target[p.x]) atomicAdd(A.counts + p.x, 1ull);
     }
 }
 
@@ -458,14 +556,14 @@ int g_num_sms = 0;
 
 extern "C" int64_t chk_entity_shadow_bytes(int rank, int64_t n_rows) {
     if (rank < 2 || n_rows <= 0) return 0;
-    const int64_t n_et = (n_rows + TILE_E - 1) / TILE_E;
+    const int64_t n_et = ((n_rows + TILE_E - 1) / TILE_E + 1) / 2 * 2;       // padded to whole tile pairs
     return n_et * (kpad_of(rank) / KC) * (int64_t)A_BLOCK + n_et * TILE_E * 4;
 }
 
 extern "C" int chk_entity_shadow_build(int rank, int64_t n_rows, const void* entity_f32, void* shadow, void* stream) {
     if (n_rows == 0) return CHK_OK;
     if (rank < 2 || n_rows < 0 || !entity_f32 || !shadow) { chk_set_error("chk_entity_shadow_build: bad argument"); return CHK_EINVAL; }
-    const int64_t n_et = (n_rows + TILE_E - 1) / TILE_E;
+    const int64_t n_et = ((n_rows + TILE_E - 1) / TILE_E + 1) / 2 * 2;       // padded to whole tile pairs (zero rows)
     if (n_et > 0x7fffffff) { chk_set_error("chk_entity_shadow_build: shard too large"); return CHK_EUNSUPPORTED; }
     const int nk = kpad_of(rank) / KC;
     uint8_t* blocks = (uint8_t*)shadow;
@@ -514,15 +612,21 @@ static int rank_mma_launch(int rank, int64_t b, const void* q, const void* qn, c
         if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || g_num_sms <= 0) {
             g_num_sms = 0; chk_set_error("CHK_RANK_MMA: no CUDA device"); return CHK_ECUDA;
         }
-        if (cudaFuncSetAttribute(rank_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL) != cudaSuccess ||
-            cudaFuncSetAttribute(rank_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL) != cudaSuccess) {
-            g_num_sms = 0; chk_set_error("CHK_RANK_MMA: cannot reserve %d bytes of shared memory: %s", SMEM_TOTAL, cudaGetErrorString(cudaGetLastError())); return CHK_ECUDA;
+        if (cudaFuncSetAttribute(rank_mma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<false>::SMEM) != cudaSuccess ||
+            cudaFuncSetAttribute(rank_mma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<false>::SMEM) != cudaSuccess ||
+            cudaFuncSetAttribute(rank_mma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<true>::SMEM) != cudaSuccess ||
+            cudaFuncSetAttribute(rank_mma_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<true>::SMEM) != cudaSuccess) {
+            g_num_sms = 0; chk_set_error("CHK_RANK_MMA: cannot reserve %d bytes of shared memory: %s", Geo<true>::SMEM, cudaGetErrorString(cudaGetLastError())); return CHK_ECUDA;
         }
     }
+    // CHK_MMA_CTA_PAIR=0 selects the single-CTA (cta_group::1) variant; default is the 2-CTA pair (cta_group::2)
+    const char* pe = getenv("CHK_MMA_CTA_PAIR");
+    const bool pair = !(pe && pe[0] == '0');
     const int nk = kpad_of(rank) / KC;
     const int64_t n_et = (n_rows + TILE_E - 1) / TILE_E;
+    const int64_t n_et_pad = (n_et + 1) / 2 * 2;
     const uint8_t* a_blocks = (const uint8_t*)shadow;
-    const float* nw = (const float*)(a_blocks + n_et * nk * (int64_t)A_BLOCK);
+    const float* nw = (const float*)(a_blocks + n_et_pad * nk * (int64_t)A_BLOCK);
     // Bound on |re~ - re_exact| (and im) relative to ||z|| ||w|| >= sum_k |z_k||w_k| (Cauchy-Schwarz):
     //   exact tier's canonical chain: 2r fused steps, each <= 2^-24 relative (standard recursive-summation bound);
     //   bf16 split: |a - hi - lo| <= 2^-18 |a| per operand plus the dropped lo*lo term -> 3 * 2^-18, rounded up to 2^-16;
@@ -541,7 +645,7 @@ static int rank_mma_launch(int rank, int64_t b, const void* q, const void* qn, c
         const float* tp = (const float*)target + b0;
         query_consts_kernel<<<(bc + 7) / 8, 256, 0, st>>>(qp, qnp, bhp, tp, bc, rank, W.qc, W.hdr);
         CHK_CUDA_LAUNCH_CHECK("query_consts_kernel");
-        query_blocks_kernel<<<dim3(nk, n_qt), 256, 0, st>>>(qp, bc, rank, nk, W.b_blocks);
+        query_blocks_kernel<<<dim3(nk, n_qt), 256, 0, st>>>(qp, bc, rank, nk, pair ? 1 : 0, W.b_blocks);
         CHK_CUDA_LAUNCH_CHECK("query_blocks_kernel");
         MmaArgs A{};
         A.a_blocks = a_blocks; A.nw = nw; A.b_blocks = W.b_blocks; A.qc = W.qc;
@@ -551,14 +655,30 @@ static int rank_mma_launch(int rank, int64_t b, const void* q, const void* qn, c
         { const char* dr = getenv("CHK_MMA_DUMP_RAW"); A.dump_raw = (dr && dr[0] == '1') ? 1 : 0; }
         A.dbg_scores = dbg_scores ? dbg_scores + b0 * n_rows : nullptr;
         A.dbg_band = dbg_band ? dbg_band + b0 * n_rows : nullptr;
-        const unsigned grid = (unsigned)(n_et < g_num_sms ? n_et : g_num_sms);
-        if (dbg_scores) rank_mma_kernel<true><<<grid, THREADS, SMEM_TOTAL, st>>>(A);
-        else rank_mma_kernel<false><<<grid, THREADS, SMEM_TOTAL, st>>>(A);
+        if (pair) {
+            const int64_t n_pairs = n_et_pad / 2, max_pairs = g_num_sms / 2;
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3((unsigned)(2 * (n_pairs < max_pairs ? n_pairs : max_pairs)));
+            cfg.blockDim = dim3(THREADS);
+            cfg.dynamicSmemBytes = Geo<true>::SMEM;
+            cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr; cfg.numAttrs = 1;
+            cudaError_t le = dbg_scores ? cudaLaunchKernelEx(&cfg, rank_mma_kernel<true, true>, A)
+                                        : cudaLaunchKernelEx(&cfg, rank_mma_kernel<false, true>, A);
+            if (le != cudaSuccess) { chk_set_error("rank_mma_kernel (cluster launch): %s", cudaGetErrorString(le)); return CHK_ECUDA; }
+        } else {
+            const unsigned grid = (unsigned)(n_et < g_num_sms ? n_et : g_num_sms);
+            if (dbg_scores) rank_mma_kernel<true, false><<<grid, THREADS, Geo<false>::SMEM, st>>>(A);
+            else rank_mma_kernel<false, false><<<grid, THREADS, Geo<false>::SMEM, st>>>(A);
+        }
         CHK_CUDA_LAUNCH_CHECK("rank_mma_kernel");
         RArgs<float> R{};
         R.q = qp; R.qn = qnp; R.bh_vals = bhp; R.target = tp; R.entity = (const float*)entity; R.hn = (const float*)hn;
         R.bt = (const float*)bt; R.b = bc; R.n_rows = n_rows; R.r = rank; R.counts = (unsigned long long*)counts + b0;
-        recheck_kernel<<<g_num_sms * 8, 128, 0, st>>>(R, W.hdr, W.list, W.list_cap);
+        recheck_kernel<<<g_num_sms * 6, RECHECK_WARPS * 32, 0, st>>>(R, W.hdr, W.list, W.list_cap);
         CHK_CUDA_LAUNCH_CHECK("recheck_kernel");
     }
     return CHK_OK;

@@ -134,6 +134,8 @@ class FFTUnitBall(KGModel):
         self.rank_algo = "fma"           # "fma" | "mma" (fp32 tcgen05 tier)
         self.process_group = None        # set to shard the entity table across ranks in get_ranking
         self._filter_cache: Dict[int, FilterIndex] = {}
+        self._eval_cache = None          # (key, ranking.EvalState): shard view, Hermitian norms, bf16 shadow
+        self._eval_ws = None
         self.fused_forward = True
 
     # ------------------------------------------------------------------ pieces of the reference API
@@ -213,6 +215,11 @@ class FFTUnitBall(KGModel):
         if isinstance(queries, np.ndarray):
             queries = torch.from_numpy(queries)
         return rank_queries(self, queries, self._filter_index(filters), batch_size)
+
+    def release_eval_cache(self):
+        """Drop the cached evaluation state (entity shadow, norms, workspace) to give the memory back."""
+        self._eval_cache = None
+        self._eval_ws = None
 
     def compute_metrics(self, examples, filters, batch_size=10):
         """models/base.py:282-322."""

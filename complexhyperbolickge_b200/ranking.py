@@ -44,6 +44,23 @@ class EvalState:
             self.shadow = ops.entity_shadow(model.rank, self.entity) if self.hi > self.lo else None
 
 
+def eval_state(model) -> EvalState:
+    """The per-pass state is a pure function of the (static during evaluation) entity / bt tables: keep it
+    across get_ranking calls until a parameter is modified in place (torch bumps ``_version``), re-allocated
+    (``data_ptr``) or the tier / sharding changes, so valid/test passes and repeated calls share one shadow."""
+    import torch.distributed as dist
+    pg = model.process_group
+    ent, bt = model.entity.weight, model.bt.weight
+    key = (ent.data_ptr(), ent._version, bt.data_ptr(), bt._version, model.rank_algo, model.bias,
+           dist.get_world_size(pg) if pg is not None else 1, dist.get_rank(pg) if pg is not None else 0)
+    hit = getattr(model, "_eval_cache", None)
+    if hit is None or hit[0] != key:
+        model._eval_cache = None                 # free the old shadow before building the new one
+        hit = (key, EvalState(model))
+        model._eval_cache = hit
+    return hit[1]
+
+
 def rank_batch(model, state: EvalState, queries_dev: torch.Tensor, indptr_dev, idx_dev, filter_total: int,
                counts: torch.Tensor, workspace=None):
     """One evaluation batch on device; counts (int64 [b]) is accumulated in place."""
@@ -75,8 +92,14 @@ def rank_queries(model, queries: torch.Tensor, findex: FilterIndex, batch_size: 
     q_np = queries.cpu().numpy() if isinstance(queries, torch.Tensor) else np.asarray(queries)
     counts_all = torch.zeros(n, dtype=torch.int64, device=dev)
     with torch.no_grad():
-        state = EvalState(model)
-        ws = ops.rank_mma_workspace(model.rank, batch_size, dev) if state.algo == ops.CHK_RANK_MMA else None
+        state = eval_state(model)
+        ws = None
+        if state.algo == ops.CHK_RANK_MMA:
+            ws = getattr(model, "_eval_ws", None)
+            if ws is None or ws[0] != (model.rank, batch_size, dev):
+                model._eval_ws = ws = ((model.rank, batch_size, dev), ops.rank_mma_workspace(model.rank, batch_size, dev))
+            ws = ws[1]
+            ops.rank_mma_reset(ws)
         for b0 in range(0, n, batch_size):
             qb = q_np[b0:b0 + batch_size]
             indptr, idx = findex.batch_csr(qb)
@@ -87,6 +110,8 @@ def rank_queries(model, queries: torch.Tensor, findex: FilterIndex, batch_size: 
             assert not torch.isnan(target).any()          # models/base.py:259-260
         if ws is not None and ops.rank_mma_status(ws)[1]:
             # the re-check list of some batch overflowed (pathological tie mass): redo the pass on the exact tier
+            state = EvalState.__new__(EvalState)
+            state.__dict__.update(eval_state(model).__dict__)
             state.algo, state.shadow = ops.CHK_RANK_FMA, None
             counts_all.zero_()
             for b0 in range(0, n, batch_size):

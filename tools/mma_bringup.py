@@ -57,6 +57,8 @@ def run(rank, n_ent, b, seed=0, regime="trained"):
 
 if __name__ == "__main__":
     torch.manual_seed(0)
+    os.environ["CHK_MMA_CTA_PAIR"] = sys.argv[1] if len(sys.argv) > 1 else "1"
+    print("CHK_MMA_CTA_PAIR =", os.environ["CHK_MMA_CTA_PAIR"])
     run(33, 1000, 150)
     run(33, 1000, 150, regime="init")
     run(65, 5000, 300)
