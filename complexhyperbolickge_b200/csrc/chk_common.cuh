@@ -147,6 +147,14 @@ template <typename T> struct RArgs {
 // the filter pass and the re-check of the tensor-core tier.
 template <typename T> struct PairTiles { T zr[32][33], zi[32][33], wr[32][33], wi[32][33]; };
 
+__device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_8(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 template <typename T>
 __device__ __forceinline__ T warp_exact_pairs(const RArgs<T>& A, unsigned i, unsigned e, bool valid, PairTiles<T>& S) {
     const int lane = threadIdx.x & 31;
@@ -155,17 +163,24 @@ __device__ __forceinline__ T warp_exact_pairs(const RArgs<T>& A, unsigned i, uns
     for (int k0 = 0; k0 < r; k0 += 32) {
         const int kc = min(32, r - k0);
         __syncwarp();
-#pragma unroll 4
+        // all 32 x 4 row segments of this chunk go out as asynchronous copies before anything is waited for
+#pragma unroll 8
         for (int p = 0; p < 32; ++p) {
             const unsigned ip = __shfl_sync(CHK_FULL, i, p), ep = __shfl_sync(CHK_FULL, e, p);
             const int vp = __shfl_sync(CHK_FULL, (int)valid, p);
             if (vp && lane < kc) {
                 const T* z = A.q + (size_t)ip * 2 * r + k0 + lane;
                 const T* w = A.entity + (size_t)ep * 2 * r + k0 + lane;
-                S.zr[p][lane] = z[0]; S.zi[p][lane] = z[r];
-                S.wr[p][lane] = w[0]; S.wi[p][lane] = w[r];
+                if (sizeof(T) == 4) {
+                    cp_async_4(&S.zr[p][lane], z); cp_async_4(&S.zi[p][lane], z + r);
+                    cp_async_4(&S.wr[p][lane], w); cp_async_4(&S.wi[p][lane], w + r);
+                } else {
+                    cp_async_8(&S.zr[p][lane], z); cp_async_8(&S.zi[p][lane], z + r);
+                    cp_async_8(&S.wr[p][lane], w); cp_async_8(&S.wi[p][lane], w + r);
+                }
             }
         }
+        cp_async_wait_all();
         __syncwarp();
         if (valid)
             for (int kk = 0; kk < kc; ++kk) dot_step<T>(S.zr[lane][kk], S.zi[lane][kk], S.wr[lane][kk], S.wi[lane][kk], re, im);

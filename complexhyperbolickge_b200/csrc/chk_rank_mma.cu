@@ -51,10 +51,19 @@ constexpr int HDR_BYTES = 256;
 constexpr unsigned SPIN_LIMIT = 1u << 28;   // bounded mbarrier spin: a protocol bug traps instead of hanging the GPU
 
 constexpr int SMEM_QC = MAX_B * 16;
+constexpr int SMEM_QNY = MAX_B * 8;
 constexpr int SMEM_CNT = MAX_B * 4;
 constexpr int SMEM_BAR = 256;
 
-__host__ __device__ inline int kpad_of(int rank) { return (2 * rank + KC - 1) / KC * KC; }
+// The MMA contracts over complex coefficients 0..r-2 only: K = 2(r-1) = n is a power of two (a multiple of KC for
+// every supported rank), operand rows are [Re_0..Re_{r-2} | Im_0..Im_{r-2}].  The last coefficient (k = r-1, the
+// Nyquist bin) is added in the epilogue with four fp32 FMAs, so no MMA work is spent on zero padding.
+__host__ __device__ inline int kpad_of(int rank) { return (2 * (rank - 1) + KC - 1) / KC * KC; }
+// column k' of an operand row -> column of the [Re | Im] source row (or -1: zero padding)
+__host__ __device__ inline int src_col(int rank, int kp) {
+    const int h = rank - 1;
+    return kp < h ? kp : (kp < 2 * h ? rank + (kp - h) : -1);
+}
 
 // byte offset of element (row, k) inside one part of a block with R rows (no-swizzle K-major canonical layout):
 // core matrix = 8 rows x 8 bf16 (128 contiguous bytes); K-adjacent core matrices R*16 bytes apart (LBO),
@@ -93,6 +102,23 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// Single-thread instructions issued from CONVERGED warps: every lane runs the surrounding (warp-uniform) control flow
+// and the instruction itself is predicated on elect.sync inside the asm block.  Keeping the roles' loops uniform lets
+// ptxas hold descriptors / addresses in uniform registers instead of serialising a divergent `if (lane == 0)` region.
+__device__ __forceinline__ void bulk_g2s_elect(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile(
+        "{\n\t.reg .pred pe;\n\t"
+        "elect.sync _|pe, 0xffffffff;\n\t"
+        "@pe cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t}"
+        ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_elect(uint32_t bar, uint32_t bytes) {
+    asm volatile(
+        "{\n\t.reg .pred pe;\n\t"
+        "elect.sync _|pe, 0xffffffff;\n\t"
+        "@pe mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}"
+        ::"r"(bar), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -137,9 +163,9 @@ __device__ __forceinline__ void split_bf16(float a, __nv_bfloat16& hi, __nv_bflo
     lo = __float2bfloat16_rn(a - __bfloat162float(hi));
 }
 
-// entity fp32 [n_rows, 2r] -> blocks[(et*nk + kc)] = { hi part | lo part } + nw[e] = ||w_e|| (rounded up)
+// entity fp32 [n_rows, 2r] -> blocks[(et*nk + kc)] = { hi part | lo part } + aux[e] = { ||w_e|| (rounded up), Re w_{r-1}, Im w_{r-1}, 0 }
 __global__ void __launch_bounds__(256) entity_shadow_kernel(const float* __restrict__ entity, int64_t n_rows, int r, int nk,
-                                                            uint8_t* __restrict__ blocks, float* __restrict__ nw) {
+                                                            uint8_t* __restrict__ blocks, float4* __restrict__ aux) {
     __shared__ float sT[TILE_E][KC + 1];
     __shared__ float sSq[TILE_E][4];
     const int64_t et = blockIdx.x;
@@ -151,8 +177,8 @@ __global__ void __launch_bounds__(256) entity_shadow_kernel(const float* __restr
         for (int idx = tid; idx < TILE_E * KC; idx += 256) {
             int row = idx / KC, kk = idx - row * KC;
             int64_t e = et * TILE_E + row;
-            int k = kc * KC + kk;
-            sT[row][kk] = (e < n_rows && k < K2) ? entity[e * K2 + k] : 0.f;
+            int k = src_col(r, kc * KC + kk);
+            sT[row][kk] = (e < n_rows && k >= 0) ? entity[e * K2 + k] : 0.f;
         }
         __syncthreads();
         uint8_t* blk = blocks + ((size_t)et * nk + kc) * A_BLOCK;
@@ -177,7 +203,10 @@ __global__ void __launch_bounds__(256) entity_shadow_kernel(const float* __restr
     __syncthreads();
     if (tid < TILE_E) {
         float s = (sSq[tid][0] + sSq[tid][1]) + (sSq[tid][2] + sSq[tid][3]);
-        nw[et * TILE_E + tid] = sqrtf(s) * (1.0f + 1e-6f);
+        const int64_t e = et * TILE_E + tid;
+        const float wrn = e < n_rows ? entity[e * K2 + r - 1] : 0.f, win = e < n_rows ? entity[e * K2 + 2 * r - 1] : 0.f;
+        s = fmaf(wrn, wrn, fmaf(win, win, s));
+        aux[e] = make_float4(sqrtf(s) * (1.0f + 1e-6f), wrn, win, 0.f);
     }
 }
 
@@ -195,11 +224,11 @@ __global__ void __launch_bounds__(256) query_blocks_kernel(const float* __restri
         __align__(16) __nv_bfloat16 h[8], l[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            int k = kc * KC + kcore * 8 + j;
+            const int kp = kc * KC + kcore * 8 + j, hh = r - 1;
             float a = 0.f;
-            if (i < b && k < K2) {
-                const float* z = q + (size_t)i * K2;
-                a = !im_row ? z[k] : (k < r ? z[r + k] : -z[k - r]);
+            if (i < b && kp < 2 * hh) {
+                const float* z = q + (size_t)i * K2;      // re-row: [Re z | Im z], im-row: [Im z | -Re z]
+                a = !im_row ? (kp < hh ? z[kp] : z[r + kp - hh]) : (kp < hh ? z[r + kp] : -z[kp - hh]);
             }
             split_bf16(a, h[j], l[j]);
         }
@@ -211,11 +240,11 @@ __global__ void __launch_bounds__(256) query_blocks_kernel(const float* __restri
     }
 }
 
-// per-query constants {2/zn, bh, target, ||z||}; also resets the re-check list counter.  One warp per query.
+// per-query constants {2/zn, bh, target, ||z||} and the batch maxima of ||z|| and |bh| (hdr[1], hdr[2]).  One warp per query.
 __global__ void __launch_bounds__(256) query_consts_kernel(const float* __restrict__ q, const float* __restrict__ qn,
                                                            const float* __restrict__ bh_vals, const float* __restrict__ target,
-                                                           int b, int r, float4* __restrict__ qc, unsigned* __restrict__ hdr) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) hdr[0] = 0u;
+                                                           int b, int r, float4* __restrict__ qc, float2* __restrict__ qny,
+                                                           unsigned* __restrict__ hdr) {
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (i >= b) return;
@@ -223,17 +252,23 @@ __global__ void __launch_bounds__(256) query_consts_kernel(const float* __restri
     float s = 0.f;
     for (int k = lane; k < 2 * r; k += 32) s = fmaf(z[k], z[k], s);
     s = warp_sum<float>(s);
-    if (lane == 0) qc[i] = make_float4(2.0f / qn[i], bh_vals ? bh_vals[i] : 0.f, target[i], sqrtf(s) * (1.0f + 1e-6f));
+    if (lane == 0) {
+        const float nz = sqrtf(s) * (1.0f + 1e-6f), bh = bh_vals ? bh_vals[i] : 0.f;
+        qc[i] = make_float4(2.0f / qn[i], bh, target[i], nz);
+        qny[i] = make_float2(z[r - 1], z[2 * r - 1]);        // Nyquist coefficient of the query
+        atomicMax(hdr + 1, __float_as_uint(nz));            // non-negative floats order like their bit patterns
+        atomicMax(hdr + 2, __float_as_uint(fabsf(bh)));
+    }
 }
 
 // ---------------------------------------------------------------------------------------------- main kernel
 struct MmaArgs {
-    const uint8_t* a_blocks; const float* nw;          // entity shadow
-    const uint8_t* b_blocks; const float4* qc;         // per-call query operands
+    const uint8_t* a_blocks; const float4* aux;        // entity shadow: operand blocks, {||w||, Re w_{r-1}, Im w_{r-1}}
+    const uint8_t* b_blocks; const float4* qc; const float2* qny;   // per-call query operands
     const float* hn; const float* bt;                  // entity side vectors (bt may be NULL)
     int64_t n_rows; int b, nk, n_et, n_qt;
     float eps_dot;                                     // |re~ - re_exact| <= eps_dot * ||z|| ||w|| (both tiers' errors)
-    unsigned* hdr; uint2* list; unsigned list_cap;     // hdr[0] = list length, hdr[1] = overflow flag (sticky)
+    unsigned* hdr; uint2* list; unsigned list_cap;     // hdr[0] = list length, hdr[1..2] = max||z||, max|bh|, hdr[4] = overflow (sticky)
     unsigned long long* counts;
     int dump_raw;                                      // DEBUG bring-up: store (re, im) instead of (score, band)
     float* dbg_scores; float* dbg_band;                // DEBUG: [b, n_rows] approximate score and band
@@ -252,28 +287,41 @@ template <bool PAIR> struct Geo {
     static constexpr int STAGE = A_BLOCK + B_BYTES;
     static constexpr int NSTAGE = PAIR ? 6 : 4;
     static constexpr int NBAR = 3 * NSTAGE + 4;                      // full, empty, peer_full, tfull[2], tempty[2]
-    static constexpr int SMEM = NSTAGE * STAGE + SMEM_QC + SMEM_CNT + SMEM_BAR;
+    static constexpr int SMEM = NSTAGE * STAGE + SMEM_QC + SMEM_QNY + SMEM_CNT + SMEM_BAR;
     static constexpr int UMMA_M = PAIR ? 2 * TILE_E : TILE_E;
 };
 
 template <bool PAIR> __device__ __forceinline__ void tc_mma_issue(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     if constexpr (PAIR) {
         asm volatile(
-            "{\n\t.reg .pred p;\n\t"
+            "{\n\t.reg .pred p, pe;\n\t"
             "setp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            "elect.sync _|pe, 0xffffffff;\n\t"
+            "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
             ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
     } else {
-        tc_mma_bf16(d_tmem, adesc, bdesc, idesc, accumulate);
+        asm volatile(
+            "{\n\t.reg .pred p, pe;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "elect.sync _|pe, 0xffffffff;\n\t"
+            "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
     }
 }
 // MMA-completion arrive; PAIR: on the barrier at this offset in BOTH CTAs of the pair
 template <bool PAIR> __device__ __forceinline__ void tc_commit_to(uint32_t bar) {
     if constexpr (PAIR) {
-        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                     ::"r"(bar), "h"((uint16_t)3) : "memory");
+        asm volatile(
+            "{\n\t.reg .pred pe;\n\t"
+            "elect.sync _|pe, 0xffffffff;\n\t"
+            "@pe tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
+            ::"r"(bar), "h"((uint16_t)3) : "memory");
     } else {
-        tc_commit(bar);
+        asm volatile(
+            "{\n\t.reg .pred pe;\n\t"
+            "elect.sync _|pe, 0xffffffff;\n\t"
+            "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+            ::"r"(bar) : "memory");
     }
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
@@ -283,6 +331,14 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 // arrive on the barrier at local address `bar` of CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster_elect(uint32_t bar, uint32_t rank) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t.reg .pred pe;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "elect.sync _|pe, 0xffffffff;\n\t"
+        "@pe mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+        ::"r"(bar), "r"(rank) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank) {
     asm volatile(
         "{\n\t.reg .b32 ra;\n\t"
@@ -312,8 +368,9 @@ __global__ void __launch_bounds__(THREADS, 1) rank_mma_kernel(const MmaArgs A) {
     constexpr int NS = G::NSTAGE;
     extern __shared__ __align__(1024) uint8_t smem[];
     float4* sQc = reinterpret_cast<float4*>(smem + NS * G::STAGE);
-    int* sCnt = reinterpret_cast<int*>(smem + NS * G::STAGE + SMEM_QC);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NS * G::STAGE + SMEM_QC + SMEM_CNT);
+    float2* sQny = reinterpret_cast<float2*>(smem + NS * G::STAGE + SMEM_QC);
+    int* sCnt = reinterpret_cast<int*>(smem + NS * G::STAGE + SMEM_QC + SMEM_QNY);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NS * G::STAGE + SMEM_QC + SMEM_QNY + SMEM_CNT);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + G::NBAR);
     const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + NS), bar_pfull = smem_u32(bars + 2 * NS);
     const uint32_t bar_tfull = smem_u32(bars + 3 * NS), bar_tempty = smem_u32(bars + 3 * NS + 2);
@@ -339,7 +396,8 @@ __global__ void __launch_bounds__(THREADS, 1) rank_mma_kernel(const MmaArgs A) {
         }
     }
     for (int i = threadIdx.x; i < MAX_B; i += THREADS) {
-        sQc[i] = i < A.b ? A.qc[i] : make_float4(-2.f, 0.f, 0.f, 0.f);
+        sQc[i] = i < A.b ? A.qc[i] : make_float4(-2.f, 0.f, __int_as_float(0x7f800000), 0.f);
+        sQny[i] = i < A.b ? A.qny[i] : make_float2(0.f, 0.f);
         sCnt[i] = 0;
     }
     tc_fence_before();
@@ -351,8 +409,8 @@ __global__ void __launch_bounds__(THREADS, 1) rank_mma_kernel(const MmaArgs A) {
     const int n_items = ((n_super - unit + n_units - 1) / n_units) * A.n_qt;
 
     if (warp == 0) {
-        // ===== producer: one elected thread issues the bulk copies of this CTA's operands =====
-        if (lane == 0) {
+        // ===== producer: the warp runs the loop converged, one elected lane issues the bulk copies =====
+        {
             int stage = 0; uint32_t phase = 0;
             for (int it = 0; it < n_items; ++it) {
                 const int sup = unit + (it / A.n_qt) * n_units, qt = it % A.n_qt;
@@ -361,18 +419,18 @@ __global__ void __launch_bounds__(THREADS, 1) rank_mma_kernel(const MmaArgs A) {
                 const uint8_t* bsrc = A.b_blocks + (size_t)qt * A.nk * B_BLOCK + (PAIR ? crank * G::B_BYTES : 0);
                 for (int kc = 0; kc < A.nk; ++kc) {
                     mbar_wait_cluster(bar_empty + 8 * stage, phase ^ 1);
-                    mbar_arrive_expect_tx(bar_full + 8 * stage, G::STAGE);
+                    mbar_arrive_expect_tx_elect(bar_full + 8 * stage, G::STAGE);
                     const uint32_t dst = stage0 + stage * G::STAGE;
-                    bulk_g2s(dst, asrc + (size_t)kc * A_BLOCK, A_BLOCK, bar_full + 8 * stage);
-                    bulk_g2s(dst + A_BLOCK, bsrc + (size_t)kc * B_BLOCK, G::B_BYTES, bar_full + 8 * stage);
+                    bulk_g2s_elect(dst, asrc + (size_t)kc * A_BLOCK, A_BLOCK, bar_full + 8 * stage);
+                    bulk_g2s_elect(dst + A_BLOCK, bsrc + (size_t)kc * B_BLOCK, G::B_BYTES, bar_full + 8 * stage);
                     if (++stage == NS) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {
             if (crank == 0) {
-                // ===== MMA issuer: one elected thread of the leader CTA =====
+                // ===== MMA issuer: warp 1 of the leader CTA, converged; one elected lane issues =====
                 constexpr uint32_t idesc = umma_idesc(G::UMMA_M, TILE_QR);
                 constexpr uint32_t a_lbo = TILE_E * 16, b_lbo = G::B_ROWS * 16, sbo = 128;   // K-step / row-group strides
                 constexpr uint32_t b_part = G::B_ROWS * KC * 2;
@@ -408,21 +466,27 @@ __global__ void __launch_bounds__(THREADS, 1) rank_mma_kernel(const MmaArgs A) {
                 for (int it = 0; it < n_items; ++it)
                     for (int kc = 0; kc < A.nk; ++kc) {
                         mbar_wait(bar_full + 8 * stage, phase);
-                        mbar_arrive_cluster(bar_pfull + 8 * stage, 0);
+                        mbar_arrive_cluster_elect(bar_pfull + 8 * stage, 0);
                         if (++stage == NS) { stage = 0; phase ^= 1; }
                     }
             }
         }
     } else if (warp >= 4) {
         // ===== epilogue: TMEM -> registers -> approximate score + band -> counts / re-check list =====
+        // Per pair (re, im from TMEM; query constants broadcast from smem; entity constants in registers):
+        //   mod2 = (re-1)^2 + im^2,  x = g mod2 - 1  (g = 2/(zn wn)),  dx >= |x~ - x_exact|,
+        //   l = lg2(xc + sqrt(xc^2-1)) (xc = max(x, 1+eps)),  s~ = bias - ln2^2 l^2,
+        //   band = (2 rho + dx) dx + slop,  rho = acosh/sqrt(x^2-1) = ln2 l rsqrt(xc^2-1)   (|d rho/dx| <= 1/3).
         const int lq = warp & 3;                       // TMEM lane quarter this warp may read
         const int chalf = (warp - 4) >> 2;             // which 128 columns (64 queries) of the tile
         const float xclamp = 1.0f + Sc<float>::ball_eps;
         const float s_clamp = score_from_x<float>(xclamp, false, 0.f, 0.f);     // exact tier's -acosh(1+eps)^2
         const float eps = A.eps_dot;
-        const float ca = 1.4142136f * eps, cb = 6.f * eps * eps;
-        constexpr float kx = 16.f * 5.9604645e-8f;                              // roundoff of (x+1) in both tiers
-        constexpr float ks1 = 3.8146973e-6f, ks2 = 9.5367432e-7f, ks3 = 2.3841858e-7f;   // 2^-18, 2^-20, 2^-22
+        const float nz_max = __uint_as_float(A.hdr[1]), bh_max = __uint_as_float(A.hdr[2]);
+        constexpr float kx = 16.f * 5.9604645e-8f;     // relative roundoff of (x+1) in both tiers
+        constexpr float LN2 = 0.69314718f, LN2SQ = 0.48045301f;
+        constexpr float k1 = (3.8146973e-6f + 4.7683716e-7f) * LN2SQ;          // (2^-18 + 2^-21) d^2: evaluation roundoff of d^2
+        const uint32_t tbase = tmem_base + ((uint32_t)(lq * 32) << 16) + chalf * 128;
         for (int it = 0; it < n_items; ++it) {
             const int sup = unit + (it / A.n_qt) * n_units, qt = it % A.n_qt;
             const int et = PAIR ? 2 * sup + (int)crank : sup;
@@ -430,62 +494,65 @@ __global__ void __launch_bounds__(THREADS, 1) rank_mma_kernel(const MmaArgs A) {
             const int64_t e = (int64_t)et * TILE_E + lq * 32 + lane;
             const bool e_ok = e < A.n_rows;
             const float iwn = e_ok ? 1.0f / A.hn[e] : -1.0f;
-            const float bte = (e_ok && A.bt) ? A.bt[e] : 0.f;
-            const float nwe = e_ok ? A.nw[e] : 0.f;
+            // rows past the end of the shard get bt = -1e30: their score can never reach a target (and stays finite)
+            const float bte = e_ok ? (A.bt ? A.bt[e] : 0.f) : -1e30f;
+            const float4 ax = e_ok ? A.aux[e] : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float nwe = ax.x, wrn = ax.y, win = ax.z;       // ||w||, Re / Im of the Nyquist coefficient
+            // dm2 = [sqrt2 eps P (1 + 4.3 eps P) + kx] (1 + mod2) >= |mod2~ - mod2| + kx mod2, P = ||z|| ||w|| <= nz_max ||w||
+            const float cae = 1.4142136f * eps * nwe * (1.0f + 4.3f * eps * nz_max * nwe);
+            // additive part of the band: 2^-21 (lg2/rsqrt approximation at small d) + 2^-22 (xc^2-1 cancellation)
+            // + 2^-22 (|bh| + |bt|) (rounding of the bias adds)
+            const float slop0 = 4.7683716e-7f + 2.3841858e-7f + 2.3841858e-7f * (fabsf(bte) + bh_max);
             mbar_wait_cluster(bar_tfull + 8 * acc, acc_phase);
             tc_fence_after();
-            int c0 = 0, c1 = 0;
-#pragma unroll 1
-            for (int g = 0; g < 4; ++g) {
-                uint32_t v[32];
-                tc_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + acc * TILE_QR + chalf * 128 + g * 32, v);
-                tc_wait_ld();
-                if (g == 3) {                          // all TMEM reads of this tile are done: hand the buffer back
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) { if constexpr (PAIR) mbar_arrive_cluster(bar_tempty + 8 * acc, 0); else mbar_arrive(bar_tempty + 8 * acc); }
-                }
-                unsigned ambmask = 0;
+            const uint32_t tacc = tbase + acc * TILE_QR;
+
+            auto process = [&](const uint32_t (&v)[32], int g) {
                 const int qbase = qt * TILE_Q + chalf * 64 + g * 16;
+                unsigned m_sure = 0, m_hi = 0;
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    const int qi = qbase + j;
-                    const float4 c = sQc[qi];                     // {2/zn, bh, target, ||z||}: warp-uniform broadcast
-                    const float re = __uint_as_float(v[2 * j]), im = __uint_as_float(v[2 * j + 1]);
-                    const float P = c.w * nwe;                    // ||z|| ||w||: delta = eps * P bounds the error of re and im
-                    const float gq = c.x * iwn;                   // 2/(zn wn) > 0
+                    const float4 c = sQc[qbase + j];              // {2/zn, bh, target (+inf beyond b), ||z||}: broadcast
+                    const float2 zn_ = sQny[qbase + j];           // coefficient r-1 is contracted here, not in the MMA
+                    const float re = fmaf(zn_.x, wrn, fmaf(zn_.y, win, __uint_as_float(v[2 * j])));
+                    const float im = fmaf(zn_.y, wrn, fmaf(-zn_.x, win, __uint_as_float(v[2 * j + 1])));
                     const float r1 = re - 1.0f;
                     const float mod2 = fmaf(r1, r1, im * im);
-                    // |mod2~ - mod2| <= 2 sqrt2 delta |zw| + 2 delta^2, |zw| <= sqrt(mod2~) + sqrt2 delta, sqrt(m) <= (1+m)/2
-                    const float dm = P * fmaf(cb, P, ca * (1.0f + mod2));
-                    const float xp1 = gq * mod2;
-                    const float x = xp1 - 1.0f;
-                    const float dx = fmaf(gq, dm, xp1 * kx);      // bound on |x~ - x_exact| (before the clamp)
-                    const bool clamped = (x + dx) <= xclamp;      // exact tier's x is clamped for sure
+                    const float pe = fmaf(c.w, cae, kx);
+                    const float dm2 = fmaf(pe, mod2, pe);
+                    const float gq = c.x * iwn;                   // 2/(zn wn) > 0
+                    const float x = fmaf(gq, mod2, -1.0f);
+                    const float dx = gq * dm2;                    // bound on |x~ - x_exact| (before the clamp)
+                    const bool clamped = (x + dx) <= xclamp;      // the exact tier's x is clamped for sure
                     const float xc = fmaxf(x, xclamp);
-                    const float xm = xc - 1.0f;
-                    const float t = xm * (xc + 1.0f);
+                    const float t = fmaf(xc, xc, -1.0f);
                     const float rs = rsqrt_approx(t);
-                    const float sq = t * rs;
-                    const float d = 0.69314718f * lg2_approx(1.0f + (xm + sq));
-                    const float rho = d * rs;                     // acosh(x)/sqrt(x^2-1) = |ds/dx| / 2
+                    const float l = lg2_approx(fmaf(t, rs, xc));
+                    const float a2 = fmaf(l * rs, 2.0f * LN2, dx);       // 2 rho + dx
+                    const float l2 = l * l;
                     const float bias = __fadd_rn(c.y, bte);
-                    const float d2 = d * d;
-                    float s = bias - d2;
-                    float band = fmaf(2.0f * (rho + dx), dx, fmaf(ks1, d2, fmaf(ks2, d, ks3 * fabsf(bias))));
+                    float band = fmaf(a2, dx, fmaf(k1, l2, slop0));
+                    float s = fmaf(-LN2SQ, l2, bias);
                     if (clamped) { s = __fadd_rn(bias, s_clamp); band = 0.f; }
-                    const bool live = e_ok && qi < A.b;
-                    const bool sure = live && (s - band >= c.z);
-                    const bool amb = live && !sure && !(s + band < c.z);      // NaN -> re-check
-                    const unsigned m = __ballot_sync(CHK_FULL, sure);
-                    if (lane == ((g * 16 + j) & 31)) { if (g < 2) c0 += __popc(m); else c1 += __popc(m); }
-                    ambmask |= amb ? (1u << j) : 0u;
+                    m_sure |= (s - band >= c.z) ? (1u << j) : 0u;             // certainly >= target
+                    m_hi |= !(s + band < c.z) ? (1u << j) : 0u;               // possibly >= target (NaN -> re-check)
                     if (DEBUG) {
-                        if (live) {
-                            A.dbg_scores[(size_t)qi * A.n_rows + e] = A.dump_raw ? re : s;
-                            A.dbg_band[(size_t)qi * A.n_rows + e] = A.dump_raw ? im : band;
+                        if (e_ok && qbase + j < A.b) {
+                            A.dbg_scores[(size_t)(qbase + j) * A.n_rows + e] = A.dump_raw ? re : s;
+                            A.dbg_band[(size_t)(qbase + j) * A.n_rows + e] = A.dump_raw ? im : band;
                         }
                     }
+                }
+                // per-query counts of this warp's 32 entities: spread 4 mask bits into 4 bytes, sum over the lanes (<= 32 per byte)
+                unsigned ambmask = m_hi & ~m_sure;
+                const unsigned r0 = __reduce_add_sync(CHK_FULL, ((m_sure & 0xFu) * 0x00204081u) & 0x01010101u);
+                const unsigned r1_ = __reduce_add_sync(CHK_FULL, (((m_sure >> 4) & 0xFu) * 0x00204081u) & 0x01010101u);
+                const unsigned r2 = __reduce_add_sync(CHK_FULL, (((m_sure >> 8) & 0xFu) * 0x00204081u) & 0x01010101u);
+                const unsigned r3 = __reduce_add_sync(CHK_FULL, (((m_sure >> 12) & 0xFu) * 0x00204081u) & 0x01010101u);
+                if (lane < 16) {
+                    const unsigned rr = lane < 8 ? (lane < 4 ? r0 : r1_) : (lane < 12 ? r2 : r3);
+                    const unsigned cnt = (rr >> (8 * (lane & 3))) & 0xffu;
+                    if (cnt) atomicAdd(&sCnt[qbase + lane], (int)cnt);
                 }
                 if (__any_sync(CHK_FULL, ambmask != 0)) {
                     while (ambmask) {
@@ -493,14 +560,20 @@ __global__ void __launch_bounds__(THREADS, 1) rank_mma_kernel(const MmaArgs A) {
                         ambmask &= ambmask - 1;
                         const unsigned slot = atomicAdd(A.hdr, 1u);
                         if (slot < A.list_cap) A.list[slot] = make_uint2((unsigned)(qbase + j), (unsigned)e);
-                        else atomicExch(A.hdr + 1, 1u);
+                        else atomicExch(A.hdr + 4, 1u);
                     }
                 }
-            }
-            // lane l owns queries (chalf*64 + l) and (chalf*64 + 32 + l) of this query tile
-            const int q0 = qt * TILE_Q + chalf * 64 + lane;
-            if (c0) atomicAdd(&sCnt[q0], c0);
-            if (c1) atomicAdd(&sCnt[q0 + 32], c1);
+            };
+
+            uint32_t va[32], vb[32];                   // TMEM loads software-pipelined one 16-query group ahead
+            tc_ld32(tacc + 0, va);  tc_wait_ld();
+            tc_ld32(tacc + 32, vb); process(va, 0); tc_wait_ld();
+            tc_ld32(tacc + 64, va); process(vb, 1); tc_wait_ld();
+            tc_ld32(tacc + 96, vb); process(va, 2); tc_wait_ld();
+            tc_fence_before();                         // all TMEM reads of this tile are done: hand the buffer back
+            __syncwarp();
+            if (lane == 0) { if constexpr (PAIR) mbar_arrive_cluster(bar_tempty + 8 * acc, 0); else mbar_arrive(bar_tempty + 8 * acc); }
+            process(vb, 3);
         }
     }
     tc_fence_before();
@@ -533,17 +606,18 @@ __global__ void __launch_bounds__(RECHECK_WARPS * 32) recheck_kernel(RArgs<float
 }
 
 struct Workspace {
-    unsigned* hdr; float4* qc; uint8_t* b_blocks; uint2* list; unsigned list_cap;
+    unsigned* hdr; float4* qc; float2* qny; uint8_t* b_blocks; uint2* list; unsigned list_cap;
 };
 
 bool carve_workspace(int rank, void* ws, int64_t bytes, Workspace& W) {
     const int nk = kpad_of(rank) / KC;
-    const int64_t fixed = HDR_BYTES + SMEM_QC + (int64_t)(MAX_B / TILE_Q) * nk * B_BLOCK;
+    const int64_t fixed = HDR_BYTES + SMEM_QC + SMEM_QNY + (int64_t)(MAX_B / TILE_Q) * nk * B_BLOCK;
     if (bytes < fixed + 8 * 1024) return false;
     uint8_t* p = (uint8_t*)ws;
     W.hdr = (unsigned*)p;
     W.qc = (float4*)(p + HDR_BYTES);
-    W.b_blocks = p + HDR_BYTES + SMEM_QC;
+    W.qny = (float2*)(p + HDR_BYTES + SMEM_QC);
+    W.b_blocks = p + HDR_BYTES + SMEM_QC + SMEM_QNY;
     W.list = (uint2*)(p + fixed);
     int64_t cap = (bytes - fixed) / 8;
     W.list_cap = (unsigned)(cap > 0x7fffffff ? 0x7fffffff : cap);
@@ -557,7 +631,7 @@ int g_num_sms = 0;
 extern "C" int64_t chk_entity_shadow_bytes(int rank, int64_t n_rows) {
     if (rank < 2 || n_rows <= 0) return 0;
     const int64_t n_et = ((n_rows + TILE_E - 1) / TILE_E + 1) / 2 * 2;       // padded to whole tile pairs
-    return n_et * (kpad_of(rank) / KC) * (int64_t)A_BLOCK + n_et * TILE_E * 4;
+    return n_et * (kpad_of(rank) / KC) * (int64_t)A_BLOCK + n_et * TILE_E * 16;
 }
 
 extern "C" int chk_entity_shadow_build(int rank, int64_t n_rows, const void* entity_f32, void* shadow, void* stream) {
@@ -567,8 +641,8 @@ extern "C" int chk_entity_shadow_build(int rank, int64_t n_rows, const void* ent
     if (n_et > 0x7fffffff) { chk_set_error("chk_entity_shadow_build: shard too large"); return CHK_EUNSUPPORTED; }
     const int nk = kpad_of(rank) / KC;
     uint8_t* blocks = (uint8_t*)shadow;
-    float* nw = (float*)(blocks + n_et * nk * (int64_t)A_BLOCK);
-    entity_shadow_kernel<<<(unsigned)n_et, 256, 0, (cudaStream_t)stream>>>((const float*)entity_f32, n_rows, rank, nk, blocks, nw);
+    float4* aux = (float4*)(blocks + n_et * nk * (int64_t)A_BLOCK);
+    entity_shadow_kernel<<<(unsigned)n_et, 256, 0, (cudaStream_t)stream>>>((const float*)entity_f32, n_rows, rank, nk, blocks, aux);
     CHK_CUDA_LAUNCH_CHECK("entity_shadow_kernel");
     return CHK_OK;
 }
@@ -576,7 +650,7 @@ extern "C" int chk_entity_shadow_build(int rank, int64_t n_rows, const void* ent
 extern "C" int64_t chk_rank_mma_workspace_bytes(int rank, int64_t b) {
     if (rank < 2) return 0;
     const int nk = kpad_of(rank) / KC;
-    const int64_t fixed = HDR_BYTES + SMEM_QC + (int64_t)(MAX_B / TILE_Q) * nk * B_BLOCK;
+    const int64_t fixed = HDR_BYTES + SMEM_QC + SMEM_QNY + (int64_t)(MAX_B / TILE_Q) * nk * B_BLOCK;
     int64_t cap = b * 8192;                      // re-check list entries
     if (cap < (1 << 20)) cap = 1 << 20;
     if (cap > (8 << 20)) cap = 8 << 20;
@@ -591,12 +665,12 @@ extern "C" int chk_rank_mma_reset(void* workspace, void* stream) {
 
 extern "C" int chk_rank_mma_status(const void* workspace, int64_t* last_list_len, int* overflowed, void* stream) {
     if (!workspace) { chk_set_error("chk_rank_mma_status: null workspace"); return CHK_EINVAL; }
-    unsigned h[2] = {0, 0};
+    unsigned h[5] = {0, 0, 0, 0, 0};
     cudaError_t e = cudaMemcpyAsync(h, workspace, sizeof(h), cudaMemcpyDeviceToHost, (cudaStream_t)stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
     if (e != cudaSuccess) { chk_set_error("chk_rank_mma_status: %s", cudaGetErrorString(e)); return CHK_ECUDA; }
     if (last_list_len) *last_list_len = h[0];
-    if (overflowed) *overflowed = (int)h[1];
+    if (overflowed) *overflowed = (int)h[4];
     return CHK_OK;
 }
 
@@ -619,14 +693,15 @@ static int rank_mma_launch(int rank, int64_t b, const void* q, const void* qn, c
             g_num_sms = 0; chk_set_error("CHK_RANK_MMA: cannot reserve %d bytes of shared memory: %s", Geo<true>::SMEM, cudaGetErrorString(cudaGetLastError())); return CHK_ECUDA;
         }
     }
-    // CHK_MMA_CTA_PAIR=0 selects the single-CTA (cta_group::1) variant; default is the 2-CTA pair (cta_group::2)
+    // CHK_MMA_CTA_PAIR=1 selects the 2-CTA pair (cta_group::2) variant.  Default is one CTA per tile: on this part the
+    // kernel is tensor-pipe / power bound either way and the single-CTA variant measured ~9 % faster.
     const char* pe = getenv("CHK_MMA_CTA_PAIR");
-    const bool pair = !(pe && pe[0] == '0');
+    const bool pair = pe && pe[0] == '1';
     const int nk = kpad_of(rank) / KC;
     const int64_t n_et = (n_rows + TILE_E - 1) / TILE_E;
     const int64_t n_et_pad = (n_et + 1) / 2 * 2;
     const uint8_t* a_blocks = (const uint8_t*)shadow;
-    const float* nw = (const float*)(a_blocks + n_et_pad * nk * (int64_t)A_BLOCK);
+    const float4* aux = (const float4*)(a_blocks + n_et_pad * nk * (int64_t)A_BLOCK);
     // Bound on |re~ - re_exact| (and im) relative to ||z|| ||w|| >= sum_k |z_k||w_k| (Cauchy-Schwarz):
     //   exact tier's canonical chain: 2r fused steps, each <= 2^-24 relative (standard recursive-summation bound);
     //   bf16 split: |a - hi - lo| <= 2^-18 |a| per operand plus the dropped lo*lo term -> 3 * 2^-18, rounded up to 2^-16;
@@ -634,7 +709,8 @@ static int rank_mma_launch(int rank, int64_t b, const void* q, const void* qn, c
     //   exact products to the fp32 accumulator with at most 2 units of 2^-23 relative to the largest magnitude
     //   involved (<= sum_k |a_k b_k|); 3 * Kpad/16 steps per accumulator.
     // tests/test_gpu_mma.py checks the observed |s~ - s| against the resulting band (it uses < 5 % of it).
-    const double eps_dot = (2.0 * rank) * 5.9604644775390625e-8 + 1.52587890625e-5 +
+    //   the Nyquist coefficient's four fp32 FMAs in the epilogue: 4 * 2^-24.
+    const double eps_dot = (2.0 * rank + 4.0) * 5.9604644775390625e-8 + 1.52587890625e-5 +
                            2.0 * (3.0 * nk * KC / 16.0) * 1.1920928955078125e-7;
     for (int64_t b0 = 0; b0 < b; b0 += MAX_B) {
         const int bc = (int)((b - b0) < MAX_B ? (b - b0) : MAX_B);
@@ -643,12 +719,13 @@ static int rank_mma_launch(int rank, int64_t b, const void* q, const void* qn, c
         const float* qnp = (const float*)qn + b0;
         const float* bhp = bh_vals ? (const float*)bh_vals + b0 : nullptr;
         const float* tp = (const float*)target + b0;
-        query_consts_kernel<<<(bc + 7) / 8, 256, 0, st>>>(qp, qnp, bhp, tp, bc, rank, W.qc, W.hdr);
+        if (cudaMemsetAsync(W.hdr, 0, 16, st) != cudaSuccess) { chk_set_error("cudaMemsetAsync failed"); return CHK_ECUDA; }
+        query_consts_kernel<<<(bc + 7) / 8, 256, 0, st>>>(qp, qnp, bhp, tp, bc, rank, W.qc, W.qny, W.hdr);
         CHK_CUDA_LAUNCH_CHECK("query_consts_kernel");
         query_blocks_kernel<<<dim3(nk, n_qt), 256, 0, st>>>(qp, bc, rank, nk, pair ? 1 : 0, W.b_blocks);
         CHK_CUDA_LAUNCH_CHECK("query_blocks_kernel");
         MmaArgs A{};
-        A.a_blocks = a_blocks; A.nw = nw; A.b_blocks = W.b_blocks; A.qc = W.qc;
+        A.a_blocks = a_blocks; A.aux = aux; A.b_blocks = W.b_blocks; A.qc = W.qc; A.qny = W.qny;
         A.hn = (const float*)hn; A.bt = (const float*)bt; A.n_rows = n_rows; A.b = bc; A.nk = nk; A.n_et = (int)n_et; A.n_qt = n_qt;
         A.eps_dot = (float)eps_dot; A.hdr = W.hdr; A.list = W.list; A.list_cap = W.list_cap;
         A.counts = (unsigned long long*)counts + b0;
