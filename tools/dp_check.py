@@ -1,0 +1,91 @@
+"""Multi-GPU check (torchrun, one rank per GPU, NCCL): (1) entity-table-sharded get_ranking equals the
+single-GPU ranks exactly; (2) a data-parallel training step (sparse row-gradient exchange) matches the
+single-GPU step on the same global batch and negatives.  Prints one line per check on rank 0.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/dp_check.py
+"""
+import os
+import sys
+from argparse import Namespace
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import complexhyperbolickge_b200 as chk  # noqa: E402
+from complexhyperbolickge_b200 import synthetic  # noqa: E402
+from complexhyperbolickge_b200.optim import N3  # noqa: E402
+from complexhyperbolickge_b200.parallel import DataParallelKGOptimizer  # noqa: E402
+
+
+class FixedNegs(DataParallelKGOptimizer):
+    negs_global = None
+
+    def get_neg_samples(self, input_batch):
+        self._negs = self.negs_global[self.rank_id::self.world].to(input_batch.device)
+        return self._negs
+
+
+def main():
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    rank, world = dist.get_rank(), dist.get_world_size()
+    for name, r, dtype, algo in (("FFTRotH", 33, "float", "mma"), ("FFTAttH", 33, "double", "fma"), ("FFTRefH", 65, "float", "mma")):
+        n_ent, n_rel2, nq = 30_011, 12, 400
+        args = Namespace(sizes=(n_ent, n_rel2, n_ent), rank=r, dropout=0, gamma=0, dtype=dtype, bias="learn",
+                         init_size=1e-3, multi_c=True)
+        model = getattr(chk, name)(args).to(dev)
+        synthetic.trained_like_(model, 0)                     # same seed -> identical replicas
+        g = torch.Generator().manual_seed(1)
+        qs = torch.stack([torch.randint(0, n_ent, (nq,), generator=g), torch.randint(0, n_rel2, (nq,), generator=g),
+                          torch.randint(0, n_ent, (nq,), generator=g)], 1)
+        filters = {(int(h), int(rr)): [int(t), int((3 * t + 1) % n_ent)] for h, rr, t in qs.numpy()}
+        model.rank_algo = algo
+        model.process_group = None
+        single = model.get_ranking(qs, filters, batch_size=128)
+        model.process_group = dist.group.WORLD
+        sharded = model.get_ranking(qs, filters, batch_size=128)
+        ok = torch.equal(single, sharded)
+        if rank == 0:
+            print(f"[ranking {name} r={r} {dtype} {algo} x{world}] sharded == single: {ok}  mean rank {single.mean().item():.2f}", flush=True)
+        assert ok
+        # ---- DP training step vs single-GPU step
+        model.process_group = None
+        B, neg = 64 * world, 50
+        batch = torch.stack([torch.randint(0, n_ent, (B,), generator=g), torch.randint(0, n_rel2, (B,), generator=g),
+                             torch.randint(0, n_ent, (B,), generator=g)], 1)
+        negs = torch.randint(0, n_ent, (B, neg), generator=g)
+        ref = getattr(chk, name)(args).to(dev)
+        ref.load_state_dict(model.state_dict())
+        o1 = FixedNegs(ref, N3(0.0), torch.optim.Adagrad(ref.parameters(), lr=0.05), B, 1, neg, False, verbose=False,
+                       process_group=None)
+        o1.world, o1.rank_id = 1, 0
+        o1.negs_global = negs
+        l1 = o1.step(batch)
+        o2 = FixedNegs(model, N3(0.0), torch.optim.Adagrad(model.parameters(), lr=0.05), B, 1, neg, False, verbose=False,
+                       process_group=dist.group.WORLD)
+        o2.negs_global = negs
+        l2 = o2.step(batch)
+        lsum = l2.clone().double()
+        dist.all_reduce(lsum)
+        tol = 1e-12 if dtype == "double" else 2e-5
+        worst = 0.0
+        for (k, a), (_, b) in zip(ref.named_parameters(), model.named_parameters()):
+            scale = max(a.detach().abs().max().item(), 1e-30)
+            worst = max(worst, (a.detach() - b.detach()).abs().max().item() / scale)
+        if rank == 0:
+            print(f"[dp step {name} r={r} {dtype} x{world}] loss single {l1.item():.9f} mean-of-ranks {lsum.item() / world:.9f}  "
+                  f"max |param diff| / max|param| after one Adagrad step = {worst:.2e}", flush=True)
+        assert abs(l1.item() - lsum.item() / world) < 1e-4 and worst < (1e-9 if dtype == "double" else 1e-4)
+        model.release_eval_cache()
+    dist.barrier()
+    if rank == 0:
+        print("dp_check ok", flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
