@@ -176,42 +176,99 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------ train leg
-def train_leg(steps, warmup, device):
-    """Drop-in training throughput on BASELINE.json configs[1]: FFTRefH rank=33 Adagrad bs=500 neg=250 on the
-    synthetic FB15k-237 shape, through the KGOptimizer contract (two model() calls, backward, torch.optim)."""
+def dp_train_leg(steps, warmup, device, pg, world):
+    """Data-parallel training (parallel.DataParallelKGOptimizer): configs[1] shape, 500 triples per rank per step
+    (weak scaling), sparse row-gradient all_gather + dense all_reduce of the relation tables over NCCL."""
     from argparse import Namespace
+    import torch.distributed as dist
     import complexhyperbolickge_b200 as chk
     from complexhyperbolickge_b200 import synthetic
-    from complexhyperbolickge_b200.optim import KGOptimizer, N3
+    from complexhyperbolickge_b200.optim import N3
+    from complexhyperbolickge_b200.parallel import DataParallelKGOptimizer
     g = synthetic.make_graph("fb237", seed=0)
     args = Namespace(sizes=(g["n_ent"], g["n_rel2"], g["n_ent"]), rank=33, dropout=0, gamma=0, dtype="float",
                      bias="learn", init_size=1e-3, multi_c=True)
     model = chk.FFTRefH(args).to(device)
     synthetic.trained_like_(model, 0)
-    opt = KGOptimizer(model, N3(0.0), torch.optim.Adagrad(model.parameters(), lr=0.02), 500, 1, 250, False, verbose=False)
+    B = 500 * world
+    opt = DataParallelKGOptimizer(model, N3(0.0), torch.optim.Adagrad(model.parameters(), lr=0.02), B, 1, 250, False,
+                                  verbose=False, process_group=pg)
     ex = synthetic.train_examples(g)
-    ex = ex[torch.randperm(ex.shape[0], generator=torch.Generator().manual_seed(0))]
-    pinned = ex[: (steps + warmup) * 500].pin_memory()
+    ex = ex[torch.randperm(ex.shape[0], generator=torch.Generator().manual_seed(0))][: (steps + warmup) * B].to(device)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     loss = None
     for i in range(steps + warmup):
         if i == warmup:
             torch.cuda.synchronize()
+            dist.barrier()
             ev0.record()
-        b = pinned[i * 500:(i + 1) * 500].to(device, non_blocking=True)
-        l = opt.calculate_loss(b)
-        l.backward()
-        opt.optimizer.step()
-        opt.optimizer.zero_grad()
-        loss = l
+        loss = opt.step(ex[i * B:(i + 1) * B])
     lv = loss.item()
     ev1.record()
     torch.cuda.synchronize()
-    ms = ev0.elapsed_time(ev1) / steps
-    return {"metric": "train_triples_per_sec", "value": 500.0 / (ms * 1e-3), "unit": "triples/s", "ms_per_step": ms,
-            "config": "BASELINE.json configs[1]: FFTRefH rank=33 Adagrad bs=500 neg=250, synthetic FB15k-237 shape, "
-                      "drop-in KGOptimizer loop (2 model() calls + backward + dense torch.optim.Adagrad)",
-            "final_loss": lv, "algorithmic_bytes_per_triple": 2 * (2 + 250) * 66 * 4}
+    t = torch.tensor([ev0.elapsed_time(ev1) / steps], device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item()
+    return {"metric": "train_triples_per_sec", "value": B / (ms * 1e-3), "unit": "triples/s", "ms_per_step": ms,
+            "scaling": "weak", "global_batch": B,
+            "config": f"BASELINE.json configs[1] shape: FFTRefH rank=33 Adagrad neg=250, 500 triples per rank x{world}, "
+                      "data parallel (sparse row-gradient all_gather + dense all_reduce of relation tables)",
+            "final_loss_rank0": lv}
+
+
+def train_leg(steps, warmup, device):
+    """Training throughput on BASELINE.json configs[1]: FFTRefH rank=33 Adagrad bs=500 neg=250 on the synthetic
+    FB15k-237 shape.  Two numbers: the fused step (train.FusedKGOptimizer: one kernel chain + row-sparse Adagrad in a
+    CUDA graph; same loss and update) and the unfused drop-in KGOptimizer contract loop (two model() calls, autograd,
+    dense torch.optim).  Each step's batch comes from pinned host memory (H2D inside the timed region)."""
+    from argparse import Namespace
+    import complexhyperbolickge_b200 as chk
+    from complexhyperbolickge_b200 import synthetic
+    from complexhyperbolickge_b200.optim import KGOptimizer, N3
+    from complexhyperbolickge_b200.train import FusedKGOptimizer
+    g = synthetic.make_graph("fb237", seed=0)
+    args = Namespace(sizes=(g["n_ent"], g["n_rel2"], g["n_ent"]), rank=33, dropout=0, gamma=0, dtype="float",
+                     bias="learn", init_size=1e-3, multi_c=True)
+    ex = synthetic.train_examples(g)
+    ex = ex[torch.randperm(ex.shape[0], generator=torch.Generator().manual_seed(0))]
+    out = {}
+    for mode, n_steps in (("fused", 10 * steps), ("drop_in", steps)):
+        model = chk.FFTRefH(args).to(device)
+        synthetic.trained_like_(model, 0)
+        cls = FusedKGOptimizer if mode == "fused" else KGOptimizer
+        opt = cls(model, N3(0.0), torch.optim.Adagrad(model.parameters(), lr=0.02), 500, 1, 250, False, verbose=False)
+        pinned = ex[: (n_steps + warmup) * 500].pin_memory()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        loss = None
+        for i in range(n_steps + warmup):
+            if i == warmup:
+                torch.cuda.synchronize()
+                if mode == "fused":
+                    opt._loss_sum.zero_()
+                ev0.record()
+            b = pinned[i * 500:(i + 1) * 500].to(device, non_blocking=True)
+            if mode == "fused":
+                opt.fused_step(b)
+            else:
+                loss = opt.calculate_loss(b)
+                loss.backward()
+                opt.optimizer.step()
+                opt.optimizer.zero_grad()
+        lv = opt._loss_sum.item() / n_steps if mode == "fused" else loss.item()
+        ev1.record()
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1) / n_steps
+        out[mode] = {"value": 500.0 / (ms * 1e-3), "ms_per_step": ms, "loss": lv}
+    bytes_per_triple = 2 * (2 + 250) * 66 * 4
+    return {"metric": "train_triples_per_sec", "value": out["fused"]["value"], "unit": "triples/s",
+            "ms_per_step": out["fused"]["ms_per_step"], "mean_loss": out["fused"]["loss"],
+            "config": "BASELINE.json configs[1]: FFTRefH rank=33 Adagrad bs=500 neg=250, synthetic FB15k-237 shape; fused step "
+                      "(K1 + K3 + loss + adjoints + row-sparse Adagrad, CUDA graph), batch H2D from pinned memory each step",
+            "algorithmic_bytes_per_triple": bytes_per_triple,
+            "hbm_frac": out["fused"]["value"] * bytes_per_triple / 1e9 / 6530.0,
+            "drop_in_contract_loop": {"value": out["drop_in"]["value"], "ms_per_step": out["drop_in"]["ms_per_step"],
+                                      "last_loss": out["drop_in"]["loss"],
+                                      "what": "unfused KGOptimizer loop: 2 model() calls + autograd + dense torch.optim.Adagrad"}}
 
 
 # ------------------------------------------------------------------------------------------------ our arm
@@ -286,10 +343,12 @@ def run_ours(args):
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         t_wall0 = time.time()
+        launches0 = ops.launch_count
         ev0.record()
         for i in range(W, W + K):
             step(i)
         ev1.record()
+        gpu_launches = ops.launch_count - launches0
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -326,6 +385,9 @@ def run_ours(args):
         torch.cuda.synchronize()
         kern_ms = k0.elapsed_time(k1) / nrep
         recheck = ops.rank_mma_status(ws) if ws is not None else (0, False)
+        shard_rows = state.hi - state.lo
+        mma = state.algo == ops.CHK_RANK_MMA
+        flops = 8.0 * rank * b * shard_rows
 
     # ---- e2e through the public API with host buffers
     e2e = None
@@ -353,6 +415,12 @@ def run_ours(args):
         e2e = {"value": b * K / (e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d // K, "d2h_bytes_per_step": b * 4,
                "api": "model.get_ranking(host LongTensor[b,3], FilterIndex, batch_size)"}
 
+    dp_train = None
+    if world > 1 and not args.no_train:
+        model.release_eval_cache()
+        del state
+        torch.cuda.empty_cache()
+        dp_train = dp_train_leg(20, 3, device, pg, world)
     if rank_id != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -362,19 +430,20 @@ def run_ours(args):
     if os.path.exists(pk):
         peaks = json.load(open(pk))
     peak_tf = peaks.get("bf16_tflops", 1590.0)
-    shard_rows = state.hi - state.lo
-    flops = 8.0 * rank * b * shard_rows
     achieved = flops / (kern_ms * 1e-3) / 1e12
-    mma = state.algo == ops.CHK_RANK_MMA
+    traffic = None                      # dram bytes per launch of the dominant kernel, from the committed ncu --set full capture
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp) and world == 1 and args.workload == "big4m" and mma:
+        traffic = json.load(open(tp)).get("rank_mma_kernel_big4m_dram_bytes_per_launch")
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                "traffic": None, "kernel": "rank_mma_kernel (tcgen05 bf16x3, incl. operand prep + exact re-check)" if mma else "rank_tile_kernel<float,1> (fp32 FMA)",
-                "kernel_ms": kern_ms, "algorithmic_flop_per_pair": 8 * rank, "issued_flop_per_pair": 8 * rank * (3 if mma else 1),
+                "traffic": traffic, "kernel": "rank_mma_kernel (tcgen05 bf16x3, incl. operand prep + exact re-check)" if mma else "rank_tile_kernel<float,1> (fp32 FMA)",
+                "kernel_ms": kern_ms, "algorithmic_flop_per_pair": 8 * rank, "issued_flop_per_pair": 8 * (rank - 1) * 3 + 8 if mma else 8 * rank,
                 "pairs_per_launch": b * shard_rows, "recheck_pairs_per_launch": recheck[0], "recheck_overflow": recheck[1],
                 "peak_source": ("MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone)" if peaks else "fallback 1.59 PFLOP/s")}
     line = {"metric": METRIC, "value": b * K / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32" if args.dtype == "float" else "f64", "data": "synthetic", "config": cfg, "clocks": clocks,
-            "e2e": e2e, "gpu_launches": 6 * K, "roofline": roofline,
+            "e2e": e2e, "gpu_launches": gpu_launches, "roofline": roofline,
             "mean_rank_check": float(ranks_check.mean())}
     if world == 1 and not args.no_cpu_baseline:
         ent_slice = min(n_ent, 250_000 if rank > 65 else 160_000)
@@ -384,8 +453,11 @@ def run_ours(args):
         line["cpu_baseline"] = {"value": 2.0 / (1.0 / v + 1.0 / v2), "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                                 "sample": f"2 x ({nq} query x {ent_slice} of {n_ent} entity rows), {t + t2:.1f} s of CPU work, "
                                           "extrapolated linearly in the table size; oracle port (torch-CPU tensors, all cores)"}
+    if dp_train is not None:
+        line["train"] = dp_train
     if world == 1 and not args.no_train:
         del state
+        model.release_eval_cache()
         torch.cuda.empty_cache()
         line["train"] = train_leg(20, 3, device)
     print(json.dumps(line), flush=True)

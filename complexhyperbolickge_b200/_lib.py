@@ -26,6 +26,10 @@ SIGNATURES = {
     "chk_query_bwd": (_i, [_i, _i, _i, _i64, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "chk_score_gather_fwd": (_i, [_i, _i, _i64, _i64, _p, _i64, _i64, _p, _p, _i64, _p, _i64, _i64, _p, _p, _p]),
     "chk_score_gather_bwd": (_i, [_i, _i, _i64, _i64, _p, _i64, _i64, _p, _p, _i64, _p, _p, _p, _p]),
+    "chk_score_gather_bwd_scatter": (_i, [_i, _i, _i64, _i64, _p, _i64, _i64, _p, _p, _p, _p, _p, _p]),
+    "chk_nsloss": (_i, [_i, _i64, _i64, _p, _p, _p, _p]),
+    "chk_sparse_adagrad": (_i, [_i, _p, _p, _p, _p, _i64, _i64, ctypes.c_double, ctypes.c_double, _p, _p, _p]),
+    "chk_step_counter_bump": (_i, [_p, _p]),
     "chk_scatter_add_rows": (_i, [_i, _p, _p, _p, _i64, _i64, _p]),
     "chk_row_hnorm": (_i, [_i, _i, _i64, _p, _p, _p]),
     "chk_score_all": (_i, [_i, _i, _i64, _p, _p, _p, _p, _p, _p, _i64, _p, _p]),

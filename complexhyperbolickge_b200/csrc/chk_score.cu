@@ -22,6 +22,7 @@ template <typename T> struct SArgs {
     int64_t B, nt; int r;
     T* scores;                       // fwd
     const T* grad_scores; T* grad_q; T* grad_rows;   // bwd
+    T* grad_dense;                   // bwd, optional: accumulate tail-row gradients straight into the dense table gradient
 };
 
 template <typename T, int NITER>
@@ -89,7 +90,8 @@ __global__ void __launch_bounds__(kWarps * 32) score_gather_kernel(SArgs<T> A) {
                 const T pz = Sc<T>::min_(sq * zn * zn * wn, -Sc<T>::ball_eps);
                 const T pw = Sc<T>::min_(sq * wn * wn * zn, -Sc<T>::ball_eps);
                 const T cz = T(4) * gd / pz, cw = T(4) * gd / pw;
-                T* grow = A.grad_rows + pair * 2 * r;
+                T* grow = A.grad_dense ? A.grad_dense + row * 2 * r : A.grad_rows + pair * 2 * r;
+                const bool scat = A.grad_dense != nullptr;
                 T* gqrow = per_pair_q ? A.grad_q + (b * A.q_stride_b + j * A.q_stride_j) * 2 * r : nullptr;
 #pragma unroll
                 for (int i = 0; i < NITER; ++i) {
@@ -99,7 +101,8 @@ __global__ void __launch_bounds__(kWarps * 32) score_gather_kernel(SArgs<T> A) {
                     T b_r = cw * (wn * (re1 * zr[i] + im * zi[i]) - mod2 * wr[i]);
                     T b_i = cw * (wn * (re1 * zi[i] - im * zr[i]) - mod2 * wi[i]);
                     if (k < r) {
-                        grow[k] = b_r; grow[r + k] = b_i;
+                        if (scat) { atomicAdd(grow + k, b_r); atomicAdd(grow + r + k, b_i); }
+                        else { grow[k] = b_r; grow[r + k] = b_i; }
                         if (per_pair_q) { gqrow[k] = a_r; gqrow[r + k] = a_i; }
                     }
                     gzr[i] += a_r; gzi[i] += a_i;
@@ -166,12 +169,34 @@ extern "C" int chk_score_gather_fwd(int dtype, int rank, int64_t B, int64_t nt,
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == CHK_F32) {
         SArgs<float> A{(const float*)q, q_stride_b, q_stride_j, (const float*)table, tail_idx, row_stride_b,
-                       (const float*)bh_vals, bh_stride_b, bh_stride_j, (const float*)bt, B, nt, rank, (float*)scores, nullptr, nullptr, nullptr};
+                       (const float*)bh_vals, bh_stride_b, bh_stride_j, (const float*)bt, B, nt, rank, (float*)scores, nullptr, nullptr, nullptr, nullptr};
         return launch_gather<float, false>(A, st);
     } else if (dtype == CHK_F64) {
         SArgs<double> A{(const double*)q, q_stride_b, q_stride_j, (const double*)table, tail_idx, row_stride_b,
-                        (const double*)bh_vals, bh_stride_b, bh_stride_j, (const double*)bt, B, nt, rank, (double*)scores, nullptr, nullptr, nullptr};
+                        (const double*)bh_vals, bh_stride_b, bh_stride_j, (const double*)bt, B, nt, rank, (double*)scores, nullptr, nullptr, nullptr, nullptr};
         return launch_gather<double, false>(A, st);
+    }
+    chk_set_error("unknown dtype %d", dtype); return CHK_EINVAL;
+}
+
+static int score_gather_bwd_impl(int dtype, int rank, int64_t B, int64_t nt,
+                                 const void* q, int64_t q_stride_b, int64_t q_stride_j,
+                                 const void* table, const int64_t* tail_idx, int64_t row_stride_b,
+                                 const void* grad_scores, void* grad_q, void* grad_rows, void* grad_dense, void* stream) {
+    if (B == 0 || nt == 0) return CHK_OK;
+    if (B < 0 || nt < 0 || rank < 2 || !q || !table || !grad_scores || !grad_q || (!grad_rows && !grad_dense) ||
+        (grad_dense && !tail_idx)) {
+        chk_set_error("chk_score_gather_bwd: bad argument"); return CHK_EINVAL;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == CHK_F32) {
+        SArgs<float> A{(const float*)q, q_stride_b, q_stride_j, (const float*)table, tail_idx, row_stride_b,
+                       nullptr, 0, 0, nullptr, B, nt, rank, nullptr, (const float*)grad_scores, (float*)grad_q, (float*)grad_rows, (float*)grad_dense};
+        return launch_gather<float, true>(A, st);
+    } else if (dtype == CHK_F64) {
+        SArgs<double> A{(const double*)q, q_stride_b, q_stride_j, (const double*)table, tail_idx, row_stride_b,
+                        nullptr, 0, 0, nullptr, B, nt, rank, nullptr, (const double*)grad_scores, (double*)grad_q, (double*)grad_rows, (double*)grad_dense};
+        return launch_gather<double, true>(A, st);
     }
     chk_set_error("unknown dtype %d", dtype); return CHK_EINVAL;
 }
@@ -180,21 +205,16 @@ extern "C" int chk_score_gather_bwd(int dtype, int rank, int64_t B, int64_t nt,
                                     const void* q, int64_t q_stride_b, int64_t q_stride_j,
                                     const void* table, const int64_t* tail_idx, int64_t row_stride_b,
                                     const void* grad_scores, void* grad_q, void* grad_rows, void* stream) {
-    if (B == 0 || nt == 0) return CHK_OK;
-    if (B < 0 || nt < 0 || rank < 2 || !q || !table || !grad_scores || !grad_q || !grad_rows) {
-        chk_set_error("chk_score_gather_bwd: bad argument"); return CHK_EINVAL;
-    }
-    cudaStream_t st = (cudaStream_t)stream;
-    if (dtype == CHK_F32) {
-        SArgs<float> A{(const float*)q, q_stride_b, q_stride_j, (const float*)table, tail_idx, row_stride_b,
-                       nullptr, 0, 0, nullptr, B, nt, rank, nullptr, (const float*)grad_scores, (float*)grad_q, (float*)grad_rows};
-        return launch_gather<float, true>(A, st);
-    } else if (dtype == CHK_F64) {
-        SArgs<double> A{(const double*)q, q_stride_b, q_stride_j, (const double*)table, tail_idx, row_stride_b,
-                        nullptr, 0, 0, nullptr, B, nt, rank, nullptr, (const double*)grad_scores, (double*)grad_q, (double*)grad_rows};
-        return launch_gather<double, true>(A, st);
-    }
-    chk_set_error("unknown dtype %d", dtype); return CHK_EINVAL;
+    return score_gather_bwd_impl(dtype, rank, B, nt, q, q_stride_b, q_stride_j, table, tail_idx, row_stride_b, grad_scores,
+                                 grad_q, grad_rows, nullptr, stream);
+}
+
+extern "C" int chk_score_gather_bwd_scatter(int dtype, int rank, int64_t B, int64_t nt,
+                                            const void* q, int64_t q_stride_b, int64_t q_stride_j,
+                                            const void* table, const int64_t* tail_idx,
+                                            const void* grad_scores, void* grad_q, void* grad_table_dense, void* stream) {
+    return score_gather_bwd_impl(dtype, rank, B, nt, q, q_stride_b, q_stride_j, table, tail_idx, 0, grad_scores,
+                                 grad_q, nullptr, grad_table_dense, stream);
 }
 
 extern "C" int chk_scatter_add_rows(int dtype, void* dense, const int64_t* idx, const void* rows,

@@ -1,0 +1,105 @@
+// Training-loop kernels next to the hot path: the negative-sampling loss with its
+// gradient, and a row-sparse Adagrad step that is exactly the dense torch.optim.Adagrad update.
+//
+//   chk_nsloss          KGOptimizer.neg_sampling_loss (reference optimizers/kg_optimizer.py:115-122):
+//                       loss = -mean(cat[logsigmoid(s[:,0]), logsigmoid(-s[:,1:])]) over B*(1+neg) terms, and d loss / d s.
+//   chk_sparse_adagrad  torch.optim.Adagrad (lr_decay = 0, weight_decay = 0): sum += g*g; p -= lr * g / (sqrt(sum) + eps)
+//                       applied only to the listed rows (a zero gradient row is a no-op in Adagrad, so sparse == dense,
+//                       SURVEY §7D), each row once per step however often it is listed, and the gradient row is cleared
+//                       so the dense .grad buffer is all-zero again without an N x 2r memset.
+#include "chk_common.cuh"
+
+namespace {
+
+template <typename T>
+__device__ __forceinline__ T logsigmoid_(T x) {           // min(x,0) - log1p(exp(-|x|)), as ATen
+    return Sc<T>::min_(x, T(0)) - Sc<T>::log1p_(Sc<T>::exp_(-Sc<T>::abs_(x)));
+}
+template <typename T>
+__device__ __forceinline__ T sigmoid_t(T x) { return T(1) / (T(1) + Sc<T>::exp_(-x)); }
+
+template <typename T>
+__global__ void __launch_bounds__(256) nsloss_kernel(const T* __restrict__ s, int64_t B, int64_t nt, T* __restrict__ loss,
+                                                     T* __restrict__ grad) {
+    __shared__ T red[8];
+    const int64_t total = B * nt;
+    const T inv = T(1) / (T)total;
+    T acc = T(0);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const bool pos = (i % nt) == 0;
+        const T x = pos ? s[i] : -s[i];                   // term = logsigmoid(x)
+        acc -= logsigmoid_<T>(x);
+        const T g = -sigmoid_t<T>(-x) * inv;              // d(-logsigmoid(x))/dx / total
+        grad[i] = pos ? g : -g;
+    }
+    acc = warp_sum<T>(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        T v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : T(0);
+        v = warp_sum<T>(v);
+        if (threadIdx.x == 0) atomicAdd(loss, v * inv);
+    }
+}
+
+// one warp per list entry; stamp[row] == *step_id marks "already updated in this step"
+template <typename T>
+__global__ void __launch_bounds__(256) sparse_adagrad_kernel(T* __restrict__ param, T* __restrict__ grad, T* __restrict__ sum,
+                                                             const int64_t* __restrict__ rows, int64_t m, int64_t width,
+                                                             T lr, T eps, int* __restrict__ stamp, const int* __restrict__ step_id) {
+    const int lane = threadIdx.x & 31;
+    const int cur = *step_id;
+    for (int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < m; t += (int64_t)gridDim.x * (blockDim.x >> 5)) {
+        const int64_t row = rows[t];
+        int first = 0;
+        if (lane == 0) first = atomicExch(stamp + row, cur) != cur;
+        first = __shfl_sync(CHK_FULL, first, 0);
+        if (!first) continue;
+        T* p = param + row * width; T* g = grad + row * width; T* a = sum + row * width;
+        for (int64_t c = lane; c < width; c += 32) {
+            const T gv = g[c];
+            const T s2 = Sc<T>::fma_(gv, gv, a[c]);
+            a[c] = s2;
+            p[c] -= lr * gv / (Sc<T>::sqrt_(s2) + eps);
+            g[c] = T(0);
+        }
+    }
+}
+
+__global__ void bump_kernel(int* c) { *c += 1; }
+
+}  // namespace
+
+extern "C" int chk_nsloss(int dtype, int64_t B, int64_t nt, const void* scores, void* loss_accum, void* grad_scores, void* stream) {
+    if (B == 0 || nt == 0) return CHK_OK;
+    if (B < 0 || nt < 0 || !scores || !loss_accum || !grad_scores) { chk_set_error("chk_nsloss: bad argument"); return CHK_EINVAL; }
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t blocks = (B * nt + 255) / 256;
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    if (dtype == CHK_F32) nsloss_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((const float*)scores, B, nt, (float*)loss_accum, (float*)grad_scores);
+    else if (dtype == CHK_F64) nsloss_kernel<double><<<(unsigned)blocks, 256, 0, st>>>((const double*)scores, B, nt, (double*)loss_accum, (double*)grad_scores);
+    else { chk_set_error("unknown dtype %d", dtype); return CHK_EINVAL; }
+    CHK_CUDA_LAUNCH_CHECK("nsloss_kernel");
+    return CHK_OK;
+}
+
+extern "C" int chk_sparse_adagrad(int dtype, void* param, void* grad, void* state_sum, const int64_t* rows, int64_t m,
+                                  int64_t width, double lr, double eps, int32_t* stamp, const int32_t* step_id, void* stream) {
+    if (m == 0 || width == 0) return CHK_OK;
+    if (m < 0 || width < 0 || !param || !grad || !state_sum || !rows || !stamp || !step_id) { chk_set_error("chk_sparse_adagrad: bad argument"); return CHK_EINVAL; }
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t blocks = (m + 7) / 8;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (dtype == CHK_F32) sparse_adagrad_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((float*)param, (float*)grad, (float*)state_sum, rows, m, width, (float)lr, (float)eps, stamp, step_id);
+    else if (dtype == CHK_F64) sparse_adagrad_kernel<double><<<(unsigned)blocks, 256, 0, st>>>((double*)param, (double*)grad, (double*)state_sum, rows, m, width, lr, eps, stamp, step_id);
+    else { chk_set_error("unknown dtype %d", dtype); return CHK_EINVAL; }
+    CHK_CUDA_LAUNCH_CHECK("sparse_adagrad_kernel");
+    return CHK_OK;
+}
+
+extern "C" int chk_step_counter_bump(int32_t* counter, void* stream) {
+    if (!counter) { chk_set_error("chk_step_counter_bump: null"); return CHK_EINVAL; }
+    bump_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(counter);
+    CHK_CUDA_LAUNCH_CHECK("bump_kernel");
+    return CHK_OK;
+}

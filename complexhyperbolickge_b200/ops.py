@@ -38,6 +38,15 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+# number of kernels of libchk_b200.so launched through these wrappers (bench.py reports the delta as gpu_launches)
+launch_count = 0
+
+
+def _launched(n: int) -> None:
+    global launch_count
+    launch_count += n
+
+
 def supported_rank(rank: int) -> bool:
     n = 2 * (rank - 1)
     return 16 <= n <= 512 and (n & (n - 1)) == 0
@@ -52,6 +61,7 @@ def query_fwd(kind, rank, multi_c, entity, rel, rel_diag, ctx, c_table, head_idx
     _lib.check(_lib.lib().chk_query_fwd(kind, _dt(entity), rank, nq, int(multi_c), _p(entity), _p(rel), _p(rel_diag),
                                         _p(ctx), _p(c_table), _p(head_idx), _p(rel_idx), _p(q), _p(c), _stream()),
                "chk_query_fwd")
+    _launched(1)
     return q, c
 
 
@@ -66,6 +76,7 @@ def query_bwd(kind, rank, multi_c, entity, rel, rel_diag, ctx, c_table, head_idx
     _lib.check(_lib.lib().chk_query_bwd(kind, _dt(entity), rank, nq, int(multi_c), _p(entity), _p(rel), _p(rel_diag),
                                         _p(ctx), _p(c_table), _p(head_idx), _p(rel_idx), _p(grad_q), _p(g_ent),
                                         _p(g_rel), _p(g_rd), _p(g_ctx), _p(g_c), _stream()), "chk_query_bwd")
+    _launched(1)
     return g_ent, g_rel, g_rd, g_ctx, g_c
 
 
@@ -75,6 +86,7 @@ def score_gather_fwd(rank, B, nt, q, q_stride_b, q_stride_j, table, tail_idx, ro
     _lib.check(_lib.lib().chk_score_gather_fwd(_dt(q), rank, B, nt, _p(q), q_stride_b, q_stride_j, _p(table),
                                                _p(tail_idx), row_stride_b, _p(bh_vals), bh_sb, bh_sj, _p(bt),
                                                _p(scores), _stream()), "chk_score_gather_fwd")
+    _launched(1)
     return scores
 
 
@@ -85,7 +97,43 @@ def score_gather_bwd(rank, B, nt, q, q_stride_b, q_stride_j, table, tail_idx, ro
     _lib.check(_lib.lib().chk_score_gather_bwd(_dt(q), rank, B, nt, _p(q), q_stride_b, q_stride_j, _p(table),
                                                _p(tail_idx), row_stride_b, _p(grad_scores), _p(grad_q),
                                                _p(grad_rows), _stream()), "chk_score_gather_bwd")
+    _launched(1)
     return grad_q, grad_rows
+
+
+def score_gather_bwd_scatter(rank, B, nt, q, q_stride_b, q_stride_j, table, tail_idx, grad_scores, grad_table_dense):
+    """K3 adjoint with the tail-row gradients accumulated straight into the dense table gradient."""
+    _chk(q, table, tail_idx, grad_scores, grad_table_dense)
+    grad_q = torch.empty_like(q)
+    _lib.check(_lib.lib().chk_score_gather_bwd_scatter(_dt(q), rank, B, nt, _p(q), q_stride_b, q_stride_j, _p(table),
+                                                       _p(tail_idx), _p(grad_scores), _p(grad_q), _p(grad_table_dense),
+                                                       _stream()), "chk_score_gather_bwd_scatter")
+    _launched(1)
+    return grad_q
+
+
+def nsloss(scores, loss_accum):
+    """Negative-sampling loss on scores [B, 1+neg] (column 0 positive): adds the mean loss to loss_accum, returns d/dscores."""
+    _chk(scores, loss_accum)
+    B, nt = scores.shape
+    grad = torch.empty_like(scores)
+    _lib.check(_lib.lib().chk_nsloss(_dt(scores), B, nt, _p(scores), _p(loss_accum), _p(grad), _stream()), "chk_nsloss")
+    _launched(1)
+    return grad
+
+
+def sparse_adagrad(param, grad, state_sum, rows, lr, eps, stamp, step_id):
+    _chk(param, grad, state_sum, rows, stamp, step_id)
+    width = param.shape[1] if param.dim() > 1 else 1
+    _lib.check(_lib.lib().chk_sparse_adagrad(_dt(param), _p(param), _p(grad), _p(state_sum), _p(rows), rows.numel(), width,
+                                             float(lr), float(eps), _p(stamp), _p(step_id), _stream()), "chk_sparse_adagrad")
+    _launched(1)
+
+
+def step_counter_bump(counter):
+    _chk(counter)
+    _lib.check(_lib.lib().chk_step_counter_bump(_p(counter), _stream()), "chk_step_counter_bump")
+    _launched(1)
 
 
 def scatter_add_rows(dense, idx, rows):
@@ -95,6 +143,7 @@ def scatter_add_rows(dense, idx, rows):
     assert rows.numel() == n_rows * width, (rows.shape, n_rows, width)
     _lib.check(_lib.lib().chk_scatter_add_rows(_dt(dense), _p(dense), _p(idx), _p(rows), n_rows, width, _stream()),
                "chk_scatter_add_rows")
+    _launched(1)
 
 
 def row_hnorm(rank, table):
@@ -102,6 +151,7 @@ def row_hnorm(rank, table):
     n = table.shape[0]
     out = torch.empty((n,), dtype=table.dtype, device=table.device)
     _lib.check(_lib.lib().chk_row_hnorm(_dt(table), rank, n, _p(table), _p(out), _stream()), "chk_row_hnorm")
+    _launched(1)
     return out
 
 
@@ -111,6 +161,7 @@ def score_all(rank, q, qn, bh_vals, entity, hn, bt):
     out = torch.empty((b, n), dtype=q.dtype, device=q.device)
     _lib.check(_lib.lib().chk_score_all(_dt(q), rank, b, _p(q), _p(qn), _p(bh_vals), _p(entity), _p(hn), _p(bt), n,
                                         _p(out), _stream()), "chk_score_all")
+    _launched(1)
     return out
 
 
@@ -120,6 +171,7 @@ def target_scores(rank, q, qn, bh_vals, tail_rows, tail_hn, tail_bt):
     out = torch.empty((b,), dtype=q.dtype, device=q.device)
     _lib.check(_lib.lib().chk_target_scores(_dt(q), rank, b, _p(q), _p(qn), _p(bh_vals), _p(tail_rows), _p(tail_hn),
                                             _p(tail_bt), _p(out), _stream()), "chk_target_scores")
+    _launched(1)
     return out
 
 
@@ -132,6 +184,7 @@ def rank_counts(algo, rank, q, qn, bh_vals, target, entity, hn, bt, shard_offset
                                           _p(entity), _p(hn), _p(bt), entity.shape[0], shard_offset,
                                           _p(filter_indptr), _p(filter_idx), filter_total, _p(shadow), _p(workspace),
                                           ws_bytes, _p(counts), _stream()), "chk_rank_counts")
+    _launched((4 * ((q.shape[0] + 1023) // 1024) if algo == CHK_RANK_MMA else (entity.shape[0] + 64 * 65535 - 1) // (64 * 65535)) + (1 if filter_total > 0 else 0))
     return counts
 
 
@@ -144,6 +197,7 @@ def entity_shadow(rank, entity):
     buf = torch.empty((nbytes,), dtype=torch.uint8, device=entity.device)
     _lib.check(_lib.lib().chk_entity_shadow_build(rank, entity.shape[0], _p(entity), _p(buf), _stream()),
                "chk_entity_shadow_build")
+    _launched(1)
     return buf
 
 

@@ -100,6 +100,7 @@ def rank_queries(model, queries: torch.Tensor, findex: FilterIndex, batch_size: 
                 model._eval_ws = ws = ((model.rank, batch_size, dev), ops.rank_mma_workspace(model.rank, batch_size, dev))
             ws = ws[1]
             ops.rank_mma_reset(ws)
+        nan_seen = torch.zeros((), dtype=torch.bool, device=dev)
         for b0 in range(0, n, batch_size):
             qb = q_np[b0:b0 + batch_size]
             indptr, idx = findex.batch_csr(qb)
@@ -107,7 +108,7 @@ def rank_queries(model, queries: torch.Tensor, findex: FilterIndex, batch_size: 
             ip = torch.from_numpy(indptr).to(dev, non_blocking=True)
             ix = torch.from_numpy(idx).to(dev, non_blocking=True) if idx.size else torch.zeros(1, dtype=torch.int64, device=dev)
             target = rank_batch(model, state, qd, ip, ix, int(idx.size), counts_all[b0:b0 + batch_size], ws)
-            assert not torch.isnan(target).any()          # models/base.py:259-260
+            nan_seen |= torch.isnan(target).any()         # models/base.py:259-260, checked once after the pass (no per-batch sync)
         if ws is not None and ops.rank_mma_status(ws)[1]:
             # the re-check list of some batch overflowed (pathological tie mass): redo the pass on the exact tier
             state = EvalState.__new__(EvalState)
@@ -124,4 +125,6 @@ def rank_queries(model, queries: torch.Tensor, findex: FilterIndex, batch_size: 
         if state.world > 1:
             import torch.distributed as dist
             dist.all_reduce(counts_all, op=dist.ReduceOp.SUM, group=model.process_group)
-    return (counts_all + 1).to(torch.float32).cpu()
+    ranks = (counts_all + 1).to(torch.float32).cpu()
+    assert not bool(nan_seen), "NaN score in get_ranking"
+    return ranks

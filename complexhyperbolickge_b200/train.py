@@ -1,0 +1,141 @@
+"""Fused negative-sampling training step behind the KGOptimizer contract.
+
+``FusedKGOptimizer`` has the constructor and the methods of ``KGOptimizer`` (optim.py; reference
+optimizers/kg_optimizer.py:14-316) and produces the same loss and the same parameter update, but ``epoch`` runs
+each batch as ONE chain of our kernels instead of two autograd graphs of eager ops:
+
+    negatives -> K1 (once: the positive and the negative call share their queries) -> K3 forward on the
+    (B, 1+neg) tails -> chk_nsloss (loss + d/dscores) -> K3 adjoint (tail-row gradients accumulated straight into the
+    dense entity gradient) -> K1 adjoint -> row scatters -> optimizer
+
+With ``torch.optim.Adagrad`` (lr_decay = 0, weight_decay = 0) the optimizer step is row-sparse and exact
+(chk_sparse_adagrad on the touched rows of every table, sharing the optimizer's own ``state['sum']`` tensors, so
+``optimizer.state_dict()`` stays valid); any other optimizer gets the dense ``.grad`` and its own ``step()``.  The
+whole chain has static shapes and is captured in a CUDA graph after the first batch (one graph launch per step; a
+ragged last batch replays eagerly).  The loss is accumulated on the device: one host sync per epoch instead of one
+per step (reference :273 ``l.item()``).  Regularisers with a non-zero weight, gradient accumulation
+(update_steps > 1) and per-negative queries fall back to the unfused contract path of the base class.
+"""
+import torch
+
+from . import ops
+from .optim import KGOptimizer
+
+
+class FusedKGOptimizer(KGOptimizer):
+    def __init__(self, *args, use_cuda_graph: bool = True, **kw):
+        super().__init__(*args, **kw)
+        m = self.model
+        w = getattr(self.regularizer, "weight", None)
+        self.fused = (w == 0 or w == 0.0) and self.update_steps == 1 and m.entity.weight.is_cuda
+        opt = self.optimizer
+        self.sparse_adagrad = (type(opt) is torch.optim.Adagrad and
+                               all(g["lr_decay"] == 0 and g["weight_decay"] == 0 and not g.get("maximize", False)
+                                   for g in opt.param_groups))
+        self.use_cuda_graph = use_cuda_graph
+        self._graph = None
+        self._static_batch = None
+        dev = m.entity.weight.device
+        self._loss_sum = torch.zeros((), dtype=m.entity.weight.dtype, device=dev)
+        self._step_id = torch.ones((), dtype=torch.int32, device=dev)
+        self._stamps = {}
+        if self.fused:
+            for p in m.parameters():                 # static dense gradient buffers, all-zero between steps
+                if p.grad is None:
+                    p.grad = torch.zeros_like(p)
+            if self.sparse_adagrad:
+                for p in m.parameters():
+                    self._stamps[p] = torch.zeros(p.shape[0], dtype=torch.int32, device=dev)
+
+    # ------------------------------------------------------------------------------------------ one fused step
+    def _forward_backward(self, batch):
+        m = self.model
+        r = m.rank
+        ent, rel, rd, cw = m.entity.weight, m.rel.weight, m.rel_diag.weight, m.c.weight
+        ctx = m._ctx_weight()
+        heads, rels = batch[:, 0].contiguous(), batch[:, 1].contiguous()
+        negs = self.get_neg_samples(batch)
+        tails = torch.cat([batch[:, 2:3], negs], 1).contiguous()
+        B, nt = tails.shape
+        learn = m.bias == "learn"
+        with torch.no_grad():
+            q, _ = ops.query_fwd(m.KIND, r, bool(m.multi_c), ent, rel, rd, ctx, cw, heads, rels)
+            bh_vals = m.bh.weight.view(-1)[heads].contiguous() if learn else None
+            scores = ops.score_gather_fwd(r, B, nt, q, 1, 0, ent, tails, 0, bh_vals, 1 if learn else 0, 0,
+                                          m.bt.weight.view(-1) if learn else None)
+            gs = ops.nsloss(scores, self._loss_sum)
+            grad_q = ops.score_gather_bwd_scatter(r, B, nt, q, 1, 0, ent, tails, gs, ent.grad)
+            g_ent, g_rel, g_rd, g_ctx, g_c = ops.query_bwd(m.KIND, r, bool(m.multi_c), ent, rel, rd, ctx, cw, heads, rels, grad_q)
+            ops.scatter_add_rows(ent.grad, heads, g_ent)
+            ops.scatter_add_rows(rel.grad, rels, g_rel)
+            ops.scatter_add_rows(rd.grad, rels, g_rd)
+            if ctx is not None:
+                ops.scatter_add_rows(ctx.grad, rels, g_ctx)
+            if m.multi_c:
+                ops.scatter_add_rows(cw.grad, rels, g_c)
+            else:
+                cw.grad += g_c.sum()
+            if learn:
+                ops.scatter_add_rows(m.bh.weight.grad, heads, gs.sum(1).contiguous())
+                ops.scatter_add_rows(m.bt.weight.grad, tails.view(-1), gs)
+        return heads, rels, tails
+
+    def _sparse_step(self, heads, rels, tails):
+        m, opt = self.model, self.optimizer
+        lr, eps = opt.param_groups[0]["lr"], opt.param_groups[0]["eps"]
+        ent_rows = torch.cat([heads, tails.view(-1)])
+        zero_row = torch.zeros(1, dtype=torch.int64, device=heads.device)
+        plan = [(m.entity.weight, ent_rows), (m.rel.weight, rels), (m.rel_diag.weight, rels),
+                (m.c.weight, rels if m.multi_c else zero_row)]
+        if m._ctx_weight() is not None:
+            plan.append((m._ctx_weight(), rels))
+        if m.bias == "learn":
+            plan += [(m.bh.weight, heads), (m.bt.weight, tails.view(-1))]
+        for p, rows in plan:
+            ops.sparse_adagrad(p.data, p.grad, opt.state[p]["sum"], rows.contiguous(), lr, eps, self._stamps[p], self._step_id)
+        ops.step_counter_bump(self._step_id)
+
+    def _step_body(self, batch):
+        heads, rels, tails = self._forward_backward(batch)
+        if self.sparse_adagrad:
+            self._sparse_step(heads, rels, tails)
+
+    def fused_step(self, batch):
+        """One training step on a device batch (B, 3); the loss is added to the device-side epoch accumulator."""
+        full = batch.shape[0] == self.batch_size
+        if self.use_cuda_graph and full:
+            if self._graph is None:
+                self._static_batch = batch.clone()
+                self._step_body(self._static_batch)           # warm-up (allocator, lazy init) — a real step
+                self._post_step()
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._step_body(self._static_batch)
+                self._graph = g
+                return                                        # the capture pass does not execute: this batch was the warm-up step
+            self._static_batch.copy_(batch)
+            self._graph.replay()
+        else:
+            self._step_body(batch)
+        self._post_step()
+
+    def _post_step(self):
+        if self.sparse_adagrad:
+            for p in self.model.parameters():                 # keep torch's bookkeeping in sync (unused when lr_decay = 0)
+                self.optimizer.state[p]["step"] += 1
+        else:
+            self.optimizer.step()
+            self.optimizer.zero_grad(set_to_none=False)
+
+    # ------------------------------------------------------------------------------------------ contract
+    def epoch(self, examples):
+        if not self.fused:
+            return super().epoch(examples)
+        actual = examples[torch.randperm(examples.shape[0]), :].to(self.device)
+        self._loss_sum.zero_()
+        n = 0
+        for b0 in range(0, examples.shape[0], self.batch_size):
+            self.fused_step(actual[b0:b0 + self.batch_size])
+            n += 1
+        return self._loss_sum.item() / max(n, 1)

@@ -76,9 +76,30 @@ int chk_score_gather_bwd(int dtype, int rank, int64_t B, int64_t nt,
                          const void* grad_scores,
                          void* grad_q, void* grad_rows, void* stream);
 
+/* Same adjoint, but the tail-row gradients are accumulated (atomic adds) straight into the DENSE gradient of the
+ * table, grad_table_dense[tail_idx[b*nt+j], :] += row gradient — no [B*nt,2r] temporary, no second pass. */
+int chk_score_gather_bwd_scatter(int dtype, int rank, int64_t B, int64_t nt,
+                                 const void* q, int64_t q_stride_b, int64_t q_stride_j,
+                                 const void* table, const int64_t* tail_idx,
+                                 const void* grad_scores, void* grad_q, void* grad_table_dense, void* stream);
+
 /* dense[idx[i], :] += rows[i, :]   (embedding_dense_backward of entity/rel/bias tables). */
 int chk_scatter_add_rows(int dtype, void* dense, const int64_t* idx, const void* rows,
                          int64_t n_rows, int64_t width, void* stream);
+
+/* ---- training-loop kernels next to the path ------------------------------
+ * Negative-sampling loss of KGOptimizer.neg_sampling_loss (optimizers/kg_optimizer.py:115-122) on scores [B,nt]
+ * whose column 0 is the positive tail: *loss_accum += -mean(cat[logsigmoid(s[:,0]), logsigmoid(-s[:,1:])]) over
+ * B*nt terms (the caller zeroes loss_accum), grad_scores [B,nt] = d loss / d scores. */
+int chk_nsloss(int dtype, int64_t B, int64_t nt, const void* scores, void* loss_accum, void* grad_scores, void* stream);
+/* Row-sparse torch.optim.Adagrad step (lr_decay = 0, weight_decay = 0; run.py:205 hands the dense tables to
+ * torch.optim): for every row listed in rows[m] — once per step even if listed several times —
+ * sum += g*g; param -= lr * g / (sqrt(sum) + eps); g = 0.  Zero-gradient rows are no-ops in Adagrad, so this equals
+ * the dense update.  stamp is an int32 [n_rows] scratch (zero-initialised once), *step_id a device counter that
+ * differs from every earlier step's value (chk_step_counter_bump). */
+int chk_sparse_adagrad(int dtype, void* param, void* grad, void* state_sum, const int64_t* rows, int64_t m,
+                       int64_t width, double lr, double eps, int32_t* stamp, const int32_t* step_id, void* stream);
+int chk_step_counter_bump(int32_t* counter, void* stream);
 
 /* ---- K2: scoring against the whole entity table + filtered rank counts (evaluation) -------------
  * All K2 entry points share ONE canonical pair-score arithmetic (ascending-k FMA chain, see
