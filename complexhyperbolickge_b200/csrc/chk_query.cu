@@ -12,6 +12,7 @@
 // layout (the packed pair IS the Givens pair), and the R2C transform is a DIT FFT (bit-reversed ->
 // natural).  No shared memory, no intermediate tensor in HBM.  Twiddles are computed once per lane with
 // sincospi in double and live in registers for the whole persistent loop.
+#include <cstdlib>
 #include "chk_common.cuh"
 
 namespace {
@@ -613,6 +614,11 @@ int launch_query(const QArgs<T>& A, cudaStream_t st) {
 
 template <typename T, int KIND, bool BWD>
 int dispatch_rank(int rank, const QArgs<T>& A, cudaStream_t st) {
+    static const bool alt = [] { const char* e = getenv("CHK_K1_ALT"); return e && e[0] == '1'; }();
+    if (alt) {      // experiment: fewer lanes per query (more points per lane, fewer shuffle stages)
+        if (rank == 33) return launch_query<T, 5, 2, KIND, BWD>(A, st);
+        if (rank == 65) return launch_query<T, 6, 3, KIND, BWD>(A, st);
+    }
     switch (rank) {
         case 9: return launch_query<T, 3, 3, KIND, BWD>(A, st);      // n=16
         case 17: return launch_query<T, 4, 3, KIND, BWD>(A, st);     // n=32

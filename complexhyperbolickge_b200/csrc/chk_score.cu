@@ -25,65 +25,83 @@ template <typename T> struct SArgs {
     T* grad_dense;                   // bwd, optional: accumulate tail-row gradients straight into the dense table gradient
 };
 
-template <typename T, int NITER>
-__device__ __forceinline__ void load_row(const T* __restrict__ row, int r, int lane, T (&re)[NITER], T (&im)[NITER]) {
+// A group of L = 2^LOGL lanes owns one (query, tail) pair: lane gl of the group holds complex coefficients
+// k = gl, gl+L, ... (P per lane), so a warp works on 32/L pairs at once and the per-pair scalar section
+// (Hermitian form, acosh, gradient coefficients) is amortised over them.  L = 8 at rank 33 (4 pairs per warp).
+template <typename T, int LOGL, int P>
+__device__ __forceinline__ void load_row(const T* __restrict__ row, int r, int gl, T (&re)[P], T (&im)[P]) {
 #pragma unroll
-    for (int i = 0; i < NITER; ++i) {
-        int k = lane + 32 * i;
-        bool ok = k < r;
+    for (int i = 0; i < P; ++i) {
+        const int k = gl + (i << LOGL);
+        const bool ok = k < r;
         re[i] = ok ? row[k] : T(0);
         im[i] = ok ? row[r + k] : T(0);
     }
 }
+template <typename T, int LOGL>
+__device__ __forceinline__ T group_sum(T v) {
+#pragma unroll
+    for (int o = (1 << LOGL) >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(CHK_FULL, v, o);
+    return v;
+}
+template <typename T, int LOGL>
+__device__ __forceinline__ void group_sum3(T& a, T& b, T& c) {
+#pragma unroll
+    for (int o = (1 << LOGL) >> 1; o > 0; o >>= 1) {
+        T ta = __shfl_xor_sync(CHK_FULL, a, o), tb = __shfl_xor_sync(CHK_FULL, b, o), tc = __shfl_xor_sync(CHK_FULL, c, o);
+        a += ta; b += tb; c += tc;
+    }
+}
 
-template <typename T, int NITER, bool BWD>
+template <typename T, int LOGL, int P, bool BWD>
 __global__ void __launch_bounds__(kWarps * 32) score_gather_kernel(SArgs<T> A) {
+    constexpr int L = 1 << LOGL, G = 32 / L;          // lanes per pair, pairs per warp
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gl = lane & (L - 1), grp = lane >> LOGL;
     const int r = A.r;
     extern __shared__ unsigned char smem_raw[];
     T* red = reinterpret_cast<T*>(smem_raw);          // [kWarps][2r] for the grad_q reduction (BWD)
     for (int64_t b = blockIdx.x; b < A.B; b += gridDim.x) {
-        T zr[NITER], zi[NITER], gzr[NITER], gzi[NITER];
+        T zr[P], zi[P], gzr[P], gzi[P];
         T zn = T(0);
         const bool per_pair_q = A.q_stride_j != 0;
         if (!per_pair_q) {
-            load_row<T, NITER>(A.q + b * A.q_stride_b * 2 * r, r, lane, zr, zi);
+            load_row<T, LOGL, P>(A.q + b * A.q_stride_b * 2 * r, r, gl, zr, zi);
             T s = T(0);
 #pragma unroll
-            for (int i = 0; i < NITER; ++i) { s = Sc<T>::fma_(zr[i], zr[i], s); s = Sc<T>::fma_(zi[i], zi[i], s); }
-            zn = clamp_hnorm<T>(warp_sum<T>(s));
+            for (int i = 0; i < P; ++i) { s = Sc<T>::fma_(zr[i], zr[i], s); s = Sc<T>::fma_(zi[i], zi[i], s); }
+            zn = clamp_hnorm<T>(group_sum<T, LOGL>(s));
         }
 #pragma unroll
-        for (int i = 0; i < NITER; ++i) { gzr[i] = T(0); gzi[i] = T(0); }
-        for (int64_t j = warp; j < A.nt; j += kWarps) {
+        for (int i = 0; i < P; ++i) { gzr[i] = T(0); gzi[i] = T(0); }
+        // U pair-groups per warp iteration: their (independent) row gathers are all issued before any is reduced
+        constexpr int U = P <= 5 ? 2 : 1;
+        auto pair_body = [&](const int64_t j, const bool valid, const int64_t row, const T (&wr)[P], const T (&wi)[P]) {
             const int64_t pair = b * A.nt + j;
-            const int64_t row = A.tail_idx ? A.tail_idx[pair] : (b * A.row_stride_b + j);
-            T wr[NITER], wi[NITER];
-            load_row<T, NITER>(A.table + row * 2 * r, r, lane, wr, wi);
             if (per_pair_q) {
-                load_row<T, NITER>(A.q + (b * A.q_stride_b + j * A.q_stride_j) * 2 * r, r, lane, zr, zi);
+                load_row<T, LOGL, P>(A.q + (b * A.q_stride_b + j * A.q_stride_j) * 2 * r, r, gl, zr, zi);
                 T s = T(0);
 #pragma unroll
-                for (int i = 0; i < NITER; ++i) { s = Sc<T>::fma_(zr[i], zr[i], s); s = Sc<T>::fma_(zi[i], zi[i], s); }
-                zn = clamp_hnorm<T>(warp_sum<T>(s));
+                for (int i = 0; i < P; ++i) { s = Sc<T>::fma_(zr[i], zr[i], s); s = Sc<T>::fma_(zi[i], zi[i], s); }
+                zn = clamp_hnorm<T>(group_sum<T, LOGL>(s));
             }
             T re = T(0), im = T(0), ws = T(0);
 #pragma unroll
-            for (int i = 0; i < NITER; ++i) {
+            for (int i = 0; i < P; ++i) {
                 dot_step<T>(zr[i], zi[i], wr[i], wi[i], re, im);
                 ws = Sc<T>::fma_(wr[i], wr[i], ws); ws = Sc<T>::fma_(wi[i], wi[i], ws);
             }
-            warp_sum3<T>(re, im, ws);
+            group_sum3<T, LOGL>(re, im, ws);
             const T wn = clamp_hnorm<T>(ws);
             const T x = clamped_x<T>(re, im, zn, wn);
             const T d = acosh_x<T>(x);
             if (!BWD) {
-                if (lane == 0) {
+                if (gl == 0 && valid) {
                     T s = -Sc<T>::mul_(d, d);
                     A.scores[pair] = A.bt ? Sc<T>::add_(Sc<T>::add_(A.bh_vals[b * A.bh_stride_b + j * A.bh_stride_j], A.bt[row]), s) : s;
                 }
             } else {
-                const T gd = T(-2) * d * A.grad_scores[pair];
+                const T gd = valid ? T(-2) * d * A.grad_scores[pair] : T(0);
                 const T re1 = re - T(1);
                 const T mod2 = Sc<T>::fma_(re1, re1, im * im);
                 const T sq = Sc<T>::sqrt_(x * x - T(1));
@@ -94,27 +112,57 @@ __global__ void __launch_bounds__(kWarps * 32) score_gather_kernel(SArgs<T> A) {
                 const bool scat = A.grad_dense != nullptr;
                 T* gqrow = per_pair_q ? A.grad_q + (b * A.q_stride_b + j * A.q_stride_j) * 2 * r : nullptr;
 #pragma unroll
-                for (int i = 0; i < NITER; ++i) {
-                    int k = lane + 32 * i;
+                for (int i = 0; i < P; ++i) {
+                    const int k = gl + (i << LOGL);
                     T a_r = cz * (zn * (re1 * wr[i] - im * wi[i]) - mod2 * zr[i]);
                     T a_i = cz * (zn * (re1 * wi[i] + im * wr[i]) - mod2 * zi[i]);
                     T b_r = cw * (wn * (re1 * zr[i] + im * zi[i]) - mod2 * wr[i]);
                     T b_i = cw * (wn * (re1 * zi[i] - im * zr[i]) - mod2 * wi[i]);
-                    if (k < r) {
+                    if (k < r && valid) {
                         if (scat) { atomicAdd(grow + k, b_r); atomicAdd(grow + r + k, b_i); }
                         else { grow[k] = b_r; grow[r + k] = b_i; }
                         if (per_pair_q) { gqrow[k] = a_r; gqrow[r + k] = a_i; }
                     }
-                    gzr[i] += a_r; gzi[i] += a_i;
+                    gzr[i] += a_r; gzi[i] += a_i;          // gd == 0 for padding groups
+                }
+            }
+        };
+        for (int64_t j0 = (int64_t)warp * G; j0 < A.nt; j0 += (int64_t)kWarps * G * U) {
+            int64_t rows[U];
+            T wr[U][P], wi[U][P];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int64_t j = j0 + (int64_t)u * kWarps * G + grp;
+                const int64_t jj = j < A.nt ? j : 0;
+                rows[u] = A.tail_idx ? A.tail_idx[b * A.nt + jj] : (b * A.row_stride_b + jj);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) load_row<T, LOGL, P>(A.table + rows[u] * 2 * r, r, gl, wr[u], wi[u]);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int64_t jb = j0 + (int64_t)u * kWarps * G;           // warp-uniform: every lane runs the shuffles
+                if (jb < A.nt) {
+                    const int64_t j = jb + grp;
+                    pair_body(j < A.nt ? j : 0, j < A.nt, rows[u], wr[u], wi[u]);
                 }
             }
         }
         if (BWD && !per_pair_q) {
-            __syncthreads();
+            // sum the per-lane partial gradients over the warp's pair groups, then over the warps
 #pragma unroll
-            for (int i = 0; i < NITER; ++i) {
-                int k = lane + 32 * i;
-                if (k < r) { red[warp * 2 * r + k] = gzr[i]; red[warp * 2 * r + r + k] = gzi[i]; }
+            for (int i = 0; i < P; ++i)
+#pragma unroll
+                for (int o = L; o < 32; o <<= 1) {
+                    gzr[i] += __shfl_xor_sync(CHK_FULL, gzr[i], o);
+                    gzi[i] += __shfl_xor_sync(CHK_FULL, gzi[i], o);
+                }
+            __syncthreads();
+            if (grp == 0) {
+#pragma unroll
+                for (int i = 0; i < P; ++i) {
+                    const int k = gl + (i << LOGL);
+                    if (k < r) { red[warp * 2 * r + k] = gzr[i]; red[warp * 2 * r + r + k] = gzi[i]; }
+                }
             }
             __syncthreads();
             T* out = A.grad_q + b * A.q_stride_b * 2 * r;
@@ -130,16 +178,17 @@ __global__ void __launch_bounds__(kWarps * 32) score_gather_kernel(SArgs<T> A) {
 
 template <typename T, bool BWD>
 int launch_gather(const SArgs<T>& A, cudaStream_t st) {
-    int niter = (A.r + 31) / 32;
     int64_t blocks = A.B < 148 * 32 ? A.B : 148 * 32;
     size_t smem = BWD ? (size_t)kWarps * 2 * A.r * sizeof(T) : 0;
-#define CHK_LAUNCH(NI)                                                                              \
-    score_gather_kernel<T, NI, BWD><<<(unsigned)blocks, kWarps * 32, smem, st>>>(A)
-    if (niter <= 1) CHK_LAUNCH(1);
-    else if (niter <= 2) CHK_LAUNCH(2);
-    else if (niter <= 3) CHK_LAUNCH(3);
-    else if (niter <= 5) CHK_LAUNCH(5);
-    else if (niter <= 9) CHK_LAUNCH(9);
+#define CHK_LAUNCH(LOGL, P)                                                                         \
+    score_gather_kernel<T, LOGL, P, BWD><<<(unsigned)blocks, kWarps * 32, smem, st>>>(A)
+    const int r = A.r;
+    if (r <= 10) CHK_LAUNCH(1, 5);            // rank 9:   2 lanes x 5
+    else if (r <= 20) CHK_LAUNCH(2, 5);       // rank 17:  4 lanes x 5
+    else if (r <= 40) CHK_LAUNCH(3, 5);       // rank 33:  8 lanes x 5 (4 pairs per warp)
+    else if (r <= 80) CHK_LAUNCH(4, 5);       // rank 65: 16 lanes x 5
+    else if (r <= 160) CHK_LAUNCH(5, 5);      // rank 129
+    else if (r <= 288) CHK_LAUNCH(5, 9);      // rank 257
     else { chk_set_error("rank %d too large", A.r); return CHK_EUNSUPPORTED; }
 #undef CHK_LAUNCH
     CHK_CUDA_LAUNCH_CHECK("score_gather_kernel");

@@ -42,29 +42,60 @@ class FilterIndex:
         gather = np.repeat(starts - new_indptr[:-1], lens) + np.arange(new_indptr[-1])
         return FilterIndex(codes[order], new_indptr, vals[gather].astype(np.int64), n_rel2)
 
+    def _normalise(self):
+        """Sort and de-duplicate every list once, so that batch lookups need no per-batch sort."""
+        if getattr(self, "_normalised", False):
+            return
+        n = len(self.keys_code)
+        if n and self.vals.size:
+            seg = np.repeat(np.arange(n, dtype=np.int64), np.diff(self.indptr))
+            order = np.lexsort((self.vals, seg))
+            seg, vals = seg[order], self.vals[order]
+            keep = np.ones(vals.size, bool)
+            keep[1:] = (seg[1:] != seg[:-1]) | (vals[1:] != vals[:-1])
+            seg, vals = seg[keep], vals[keep]
+            indptr = np.zeros(n + 1, dtype=np.int64)
+            np.cumsum(np.bincount(seg, minlength=n), out=indptr[1:])
+            self.indptr, self.vals = indptr, vals.astype(np.int64)
+        self._normalised = True
+
     def batch_csr(self, queries: np.ndarray, strict: bool = True):
         """queries int64 [b,3] -> (indptr [b+1], idx [total]) with idx_i = unique(filter[(h,r)] ∪ {t}), sorted.
 
-        strict=True mirrors the reference's KeyError when a query key is absent (models/base.py:266)."""
+        strict=True mirrors the reference's KeyError when a query key is absent (models/base.py:266).
+        O(total) vectorised work per batch: the stored lists are sorted and unique (normalised once), the true
+        tail is merged in by position."""
+        self._normalise()
         b = queries.shape[0]
+        nk = len(self.keys_code)
         code = queries[:, 0].astype(np.int64) * self.n_rel2 + queries[:, 1].astype(np.int64)
-        pos = np.searchsorted(self.keys_code, code)
-        pos_c = np.minimum(pos, max(len(self.keys_code) - 1, 0))
-        found = (len(self.keys_code) > 0) & (self.keys_code[pos_c] == code) if len(self.keys_code) else np.zeros(b, bool)
+        if nk:
+            pos = np.minimum(np.searchsorted(self.keys_code, code), nk - 1)
+            found = self.keys_code[pos] == code
+        else:
+            pos, found = np.zeros(b, np.int64), np.zeros(b, bool)
         if strict and not np.all(found):
             bad = queries[np.argmin(found)]
             raise KeyError((int(bad[0]), int(bad[1])))
-        starts = np.where(found, self.indptr[pos_c], 0)
-        lens = np.where(found, self.indptr[pos_c + 1] - self.indptr[pos_c], 0) if len(self.keys_code) else np.zeros(b, np.int64)
+        starts = np.where(found, self.indptr[pos], 0) if nk else np.zeros(b, np.int64)
+        lens = np.where(found, self.indptr[pos + 1] - self.indptr[pos], 0) if nk else np.zeros(b, np.int64)
+        tails = queries[:, 2].astype(np.int64)
         tot = int(lens.sum())
         off = np.zeros(b + 1, dtype=np.int64)
         np.cumsum(lens, out=off[1:])
-        src = np.repeat(starts - off[:-1], lens) + np.arange(tot)
-        ent = np.concatenate([self.vals[src], queries[:, 2].astype(np.int64)])
-        qid = np.concatenate([np.repeat(np.arange(b, dtype=np.int64), lens), np.arange(b, dtype=np.int64)])
-        n_ent = int(ent.max()) + 1 if ent.size else 1
-        key = np.unique(qid * n_ent + ent)
-        qid_u, ent_u = key // n_ent, key % n_ent
+        qid = np.repeat(np.arange(b, dtype=np.int64), lens)
+        ent = self.vals[np.repeat(starts - off[:-1], lens) + np.arange(tot)] if tot else np.zeros(0, np.int64)
+        t_rep = tails[qid]
+        present = np.zeros(b, bool)
+        present[qid[ent == t_rep]] = True
+        below = np.bincount(qid[ent < t_rep], minlength=b) if tot else np.zeros(b, np.int64)   # insertion position of t
+        add = (~present).astype(np.int64)
+        out_lens = lens + add
         indptr = np.zeros(b + 1, dtype=np.int64)
-        np.cumsum(np.bincount(qid_u, minlength=b), out=indptr[1:])
-        return indptr, ent_u.astype(np.int64)
+        np.cumsum(out_lens, out=indptr[1:])
+        idx = np.empty(int(indptr[-1]), dtype=np.int64)
+        shift = (add[qid] == 1) & (ent > t_rep)                 # entries after an inserted tail move one slot
+        idx[indptr[:-1][qid] + (np.arange(tot) - off[:-1][qid]) + shift] = ent
+        ins = np.nonzero(add)[0]
+        idx[indptr[:-1][ins] + below[ins]] = tails[ins]
+        return indptr, idx
