@@ -220,15 +220,16 @@ def dp_train_leg(steps, warmup, device, pg, world):
     import complexhyperbolickge_b200 as chk
     from complexhyperbolickge_b200 import synthetic
     from complexhyperbolickge_b200.optim import N3
-    from complexhyperbolickge_b200.parallel import DataParallelKGOptimizer
+    from complexhyperbolickge_b200.parallel import FusedDataParallelKGOptimizer
     g = synthetic.make_graph("fb237", seed=0)
     args = Namespace(sizes=(g["n_ent"], g["n_rel2"], g["n_ent"]), rank=33, dropout=0, gamma=0, dtype="float",
                      bias="learn", init_size=1e-3, multi_c=True)
     model = chk.FFTRefH(args).to(device)
     synthetic.trained_like_(model, 0)
     B = 500 * world
-    opt = DataParallelKGOptimizer(model, N3(0.0), torch.optim.Adagrad(model.parameters(), lr=0.02), B, 1, 250, False,
-                                  verbose=False, process_group=pg)
+    opt = FusedDataParallelKGOptimizer(model, N3(0.0), torch.optim.Adagrad(model.parameters(), lr=0.02), B, 1, 250, False,
+                                       verbose=False, process_group=pg)
+    steps *= 10
     ex = synthetic.train_examples(g)
     ex = ex[torch.randperm(ex.shape[0], generator=torch.Generator().manual_seed(0))][: (steps + warmup) * B].to(device)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -238,8 +239,8 @@ def dp_train_leg(steps, warmup, device, pg, world):
             torch.cuda.synchronize()
             dist.barrier()
             ev0.record()
-        loss = opt.step(ex[i * B:(i + 1) * B])
-    lv = loss.item()
+        opt.step(ex[i * B:(i + 1) * B])
+    lv = opt._loss_sum.item() / (steps + warmup)
     ev1.record()
     torch.cuda.synchronize()
     t = torch.tensor([ev0.elapsed_time(ev1) / steps], device=device)
@@ -248,8 +249,9 @@ def dp_train_leg(steps, warmup, device, pg, world):
     return {"metric": "train_triples_per_sec", "value": B / (ms * 1e-3), "unit": "triples/s", "ms_per_step": ms,
             "scaling": "weak", "global_batch": B,
             "config": f"BASELINE.json configs[1] shape: FFTRefH rank=33 Adagrad neg=250, 500 triples per rank x{world}, "
-                      "data parallel (sparse row-gradient all_gather + dense all_reduce of relation tables)",
-            "final_loss_rank0": lv}
+                      "fused step per rank (CUDA graph) + all_gather of touched row ids + dense all_reduce of the (small) table gradients "
+                      "[sparse row exchange for tables larger than the touched rows] + row-sparse Adagrad on the union",
+            "mean_loss_rank0": lv}
 
 
 def train_leg(steps, warmup, device):

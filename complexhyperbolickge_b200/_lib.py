@@ -17,6 +17,14 @@ CHK_F32, CHK_F64 = 0, 1
 CHK_RANK_FMA, CHK_RANK_MMA = 0, 1
 
 _i, _i64, _p = ctypes.c_int, ctypes.c_int64, ctypes.c_void_p
+CHK_MAX_TABLES = 8
+
+
+class TableDesc(ctypes.Structure):
+    """chk_table_desc of include/chk_b200.h."""
+    _fields_ = [("param", _p), ("grad", _p), ("state_sum", _p), ("rows", _p), ("m", _i64), ("src_rows", _p),
+                ("width", _i64), ("stamp", _p)]
+
 
 # name -> (restype, argtypes); mirrors include/chk_b200.h line by line
 SIGNATURES = {
@@ -30,6 +38,8 @@ SIGNATURES = {
     "chk_nsloss": (_i, [_i, _i64, _i64, _p, _p, _p, _p]),
     "chk_sparse_adagrad": (_i, [_i, _p, _p, _p, _p, _i64, _i64, ctypes.c_double, ctypes.c_double, _p, _p, _p]),
     "chk_step_counter_bump": (_i, [_p, _p]),
+    "chk_multi_scatter_add": (_i, [_i, ctypes.POINTER(TableDesc), _i, _p]),
+    "chk_multi_sparse_adagrad": (_i, [_i, ctypes.POINTER(TableDesc), _i, ctypes.c_double, ctypes.c_double, _p, _p]),
     "chk_scatter_add_rows": (_i, [_i, _p, _p, _p, _i64, _i64, _p]),
     "chk_row_hnorm": (_i, [_i, _i, _i64, _p, _p, _p]),
     "chk_score_all": (_i, [_i, _i, _i64, _p, _p, _p, _p, _p, _p, _i64, _p, _p]),

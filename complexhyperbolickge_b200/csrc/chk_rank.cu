@@ -145,15 +145,16 @@ __global__ void __launch_bounds__(256) rank_tile_kernel(RArgs<T> A) {
 
 // ---- per-pair exact kernels (canonical chain exact_pair(), one thread per pair) ---------------------
 
-// target[i] = score(q_i, tail_rows_i)
+// target[i] = score(q_i, tail_rows_i): pair (i, i) of the gathered tail rows, one lane per query, rows staged by the warp
 template <typename T>
-__global__ void target_kernel(const T* q, const T* qn, const T* bh_vals, const T* tail_rows, const T* tail_hn,
-                              const T* tail_bt, int64_t b, int r, T* target) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= b) return;
-    bool has_bias = tail_bt != nullptr;
-    target[i] = exact_pair<T>(q + i * 2 * r, tail_rows + i * 2 * r, r, qn[i], tail_hn[i], has_bias,
-                              has_bias ? bh_vals[i] : T(0), has_bias ? tail_bt[i] : T(0));
+__global__ void __launch_bounds__(32) target_kernel(RArgs<T> A, T* __restrict__ target) {
+    __shared__ PairTiles<T> S;
+    for (int64_t i0 = (int64_t)blockIdx.x * 32; i0 < A.b; i0 += (int64_t)gridDim.x * 32) {
+        const int64_t i = i0 + threadIdx.x;
+        const bool valid = i < A.b;
+        const T s = warp_exact_pairs<T>(A, (unsigned)(valid ? i : 0), (unsigned)(valid ? i : 0), valid, S);
+        if (valid) target[i] = s;
+    }
 }
 
 // counts[i] -= #{ e in filter_i within the shard : score(i,e) >= target[i] }; one lane per filter entry, rows
@@ -253,9 +254,11 @@ extern "C" int chk_target_scores(int dtype, int rank, int64_t b, const void* q, 
         chk_set_error("chk_target_scores: bad argument"); return CHK_EINVAL;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    unsigned blocks = (unsigned)((b + 127) / 128);
-    if (dtype == CHK_F32) target_kernel<float><<<blocks, 128, 0, st>>>((const float*)q, (const float*)qn, (const float*)bh_vals, (const float*)tail_rows, (const float*)tail_hn, (const float*)tail_bt, b, rank, (float*)target);
-    else if (dtype == CHK_F64) target_kernel<double><<<blocks, 128, 0, st>>>((const double*)q, (const double*)qn, (const double*)bh_vals, (const double*)tail_rows, (const double*)tail_hn, (const double*)tail_bt, b, rank, (double*)target);
+    unsigned blocks = (unsigned)((b + 31) / 32);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    // the gathered tail rows play the entity table: pair (i, i), hn = tail_hn, bt = tail_bt
+    if (dtype == CHK_F32) { auto A = make_rargs<float>(rank, b, q, qn, bh_vals, nullptr, tail_rows, tail_hn, tail_bt, b); target_kernel<float><<<blocks, 32, 0, st>>>(A, (float*)target); }
+    else if (dtype == CHK_F64) { auto A = make_rargs<double>(rank, b, q, qn, bh_vals, nullptr, tail_rows, tail_hn, tail_bt, b); target_kernel<double><<<blocks, 32, 0, st>>>(A, (double*)target); }
     else { chk_set_error("unknown dtype %d", dtype); return CHK_EINVAL; }
     CHK_CUDA_LAUNCH_CHECK("target_kernel");
     return CHK_OK;

@@ -68,6 +68,44 @@ __global__ void __launch_bounds__(256) sparse_adagrad_kernel(T* __restrict__ par
 
 __global__ void bump_kernel(int* c) { *c += 1; }
 
+// ---- multi-table variants: one launch walks up to CHK_MAX_TABLES tables (blockIdx.y = table) ---------------------
+struct TabList { chk_table_desc t[CHK_MAX_TABLES]; };
+
+template <typename T>
+__global__ void __launch_bounds__(256) multi_scatter_kernel(TabList L) {
+    const chk_table_desc d = L.t[blockIdx.y];
+    if (!d.src_rows) return;
+    T* dense = (T*)d.grad; const T* src = (const T*)d.src_rows;
+    const int64_t total = d.m * d.width;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t rrow = i / d.width, c = i - rrow * d.width;
+        atomicAdd(dense + d.rows[rrow] * d.width + c, src[i]);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) multi_adagrad_kernel(TabList L, T lr, T eps, const int* __restrict__ step_id) {
+    const chk_table_desc d = L.t[blockIdx.y];
+    const int lane = threadIdx.x & 31;
+    const int cur = *step_id;
+    T* param = (T*)d.param; T* grad = (T*)d.grad; T* sum = (T*)d.state_sum;
+    for (int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < d.m; t += (int64_t)gridDim.x * (blockDim.x >> 5)) {
+        const int64_t row = d.rows[t];
+        int first = 0;
+        if (lane == 0) first = atomicExch(d.stamp + row, cur) != cur;
+        first = __shfl_sync(CHK_FULL, first, 0);
+        if (!first) continue;
+        T* p = param + row * d.width; T* g = grad + row * d.width; T* a = sum + row * d.width;
+        for (int64_t c = lane; c < d.width; c += 32) {
+            const T gv = g[c];
+            const T s2 = Sc<T>::fma_(gv, gv, a[c]);
+            a[c] = s2;
+            p[c] -= lr * gv / (Sc<T>::sqrt_(s2) + eps);
+            g[c] = T(0);
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" int chk_nsloss(int dtype, int64_t B, int64_t nt, const void* scores, void* loss_accum, void* grad_scores, void* stream) {
@@ -101,5 +139,51 @@ extern "C" int chk_step_counter_bump(int32_t* counter, void* stream) {
     if (!counter) { chk_set_error("chk_step_counter_bump: null"); return CHK_EINVAL; }
     bump_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(counter);
     CHK_CUDA_LAUNCH_CHECK("bump_kernel");
+    return CHK_OK;
+}
+
+static int check_tabs(const chk_table_desc* tabs, int n, bool need_src, bool need_opt, TabList& L, int64_t& max_items, int64_t per_block) {
+    if (n < 1 || n > CHK_MAX_TABLES || !tabs) { chk_set_error("multi-table call: 1..%d tables expected", CHK_MAX_TABLES); return CHK_EINVAL; }
+    max_items = 0;
+    for (int i = 0; i < n; ++i) {
+        const chk_table_desc& d = tabs[i];
+        if (d.m < 0 || d.width <= 0 || !d.grad || (d.m > 0 && !d.rows) || (need_opt && (!d.param || !d.state_sum || !d.stamp))) {
+            chk_set_error("multi-table call: bad descriptor %d", i); return CHK_EINVAL;
+        }
+        L.t[i] = d;
+        const int64_t items = need_src ? (d.src_rows ? d.m * d.width : 0) : d.m;
+        if (items > max_items) max_items = items;
+    }
+    (void)per_block;
+    return CHK_OK;
+}
+
+extern "C" int chk_multi_scatter_add(int dtype, const chk_table_desc* tabs, int n_tables, void* stream) {
+    TabList L{}; int64_t mx = 0;
+    int rc = check_tabs(tabs, n_tables, true, false, L, mx, 256);
+    if (rc != CHK_OK) return rc;
+    if (mx == 0) return CHK_OK;
+    int64_t bx = (mx + 255) / 256; if (bx > 148 * 4) bx = 148 * 4;
+    dim3 grid((unsigned)bx, (unsigned)n_tables);
+    if (dtype == CHK_F32) multi_scatter_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(L);
+    else if (dtype == CHK_F64) multi_scatter_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>(L);
+    else { chk_set_error("unknown dtype %d", dtype); return CHK_EINVAL; }
+    CHK_CUDA_LAUNCH_CHECK("multi_scatter_kernel");
+    return CHK_OK;
+}
+
+extern "C" int chk_multi_sparse_adagrad(int dtype, const chk_table_desc* tabs, int n_tables, double lr, double eps,
+                                        const int32_t* step_id, void* stream) {
+    TabList L{}; int64_t mx = 0;
+    if (!step_id) { chk_set_error("chk_multi_sparse_adagrad: null step_id"); return CHK_EINVAL; }
+    int rc = check_tabs(tabs, n_tables, false, true, L, mx, 8);
+    if (rc != CHK_OK) return rc;
+    if (mx == 0) return CHK_OK;
+    int64_t bx = (mx + 7) / 8; if (bx > 148 * 8) bx = 148 * 8;
+    dim3 grid((unsigned)bx, (unsigned)n_tables);
+    if (dtype == CHK_F32) multi_adagrad_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(L, (float)lr, (float)eps, step_id);
+    else if (dtype == CHK_F64) multi_adagrad_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>(L, lr, eps, step_id);
+    else { chk_set_error("unknown dtype %d", dtype); return CHK_EINVAL; }
+    CHK_CUDA_LAUNCH_CHECK("multi_adagrad_kernel");
     return CHK_OK;
 }

@@ -130,6 +130,36 @@ def sparse_adagrad(param, grad, state_sum, rows, lr, eps, stamp, step_id):
     _launched(1)
 
 
+def _descs(tables):
+    """tables: list of dicts(param=, grad=, state_sum=, rows=, src_rows=, stamp=) of CUDA tensors (or None)."""
+    arr = (_lib.TableDesc * len(tables))()
+    for d, t in zip(arr, tables):
+        g = t["grad"]
+        _chk(t.get("param"), g, t.get("state_sum"), t["rows"], t.get("src_rows"), t.get("stamp"))
+        d.param, d.grad, d.state_sum = _p(t.get("param")), _p(g), _p(t.get("state_sum"))
+        d.rows, d.m, d.src_rows = _p(t["rows"]), t["rows"].numel(), _p(t.get("src_rows"))
+        d.width = g.shape[1] if g.dim() > 1 else 1
+        d.stamp = _p(t.get("stamp"))
+        if t.get("src_rows") is not None:
+            assert t["src_rows"].numel() == d.m * d.width, (t["src_rows"].shape, d.m, d.width)
+    return arr
+
+
+def multi_scatter_add(tables):
+    """grad[rows] += src_rows for several tables in one launch."""
+    arr = _descs(tables)
+    _lib.check(_lib.lib().chk_multi_scatter_add(_dt(tables[0]["grad"]), arr, len(tables), _stream()), "chk_multi_scatter_add")
+    _launched(1)
+
+
+def multi_sparse_adagrad(tables, lr, eps, step_id):
+    arr = _descs(tables)
+    _chk(step_id)
+    _lib.check(_lib.lib().chk_multi_sparse_adagrad(_dt(tables[0]["grad"]), arr, len(tables), float(lr), float(eps),
+                                                   _p(step_id), _stream()), "chk_multi_sparse_adagrad")
+    _launched(1)
+
+
 def step_counter_bump(counter):
     _chk(counter)
     _lib.check(_lib.lib().chk_step_counter_bump(_p(counter), _stream()), "chk_step_counter_bump")

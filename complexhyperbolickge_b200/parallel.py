@@ -19,7 +19,9 @@ from typing import Dict, Iterable, List, Optional
 import torch
 import torch.distributed as dist
 
+from . import ops
 from .optim import KGOptimizer
+from .train import FusedKGOptimizer
 
 SPARSE_TABLES = ("entity", "bh", "bt")
 
@@ -131,3 +133,68 @@ class DataParallelKGOptimizer(KGOptimizer):
             dist.all_reduce(total, op=dist.ReduceOp.SUM, group=self.pg)
             total /= self.world
         return (total / max(n, 1)).item()
+
+
+class FusedDataParallelKGOptimizer(FusedKGOptimizer):
+    """Data-parallel version of the fused step (train.FusedKGOptimizer) for ``torch.optim.Adagrad``: every rank runs
+    the fused forward/backward chain on rows ``rank::world`` of the global batch (captured in a CUDA graph), then
+
+    * the touched row ids of every rank are all_gathered (fixed size, no host sync),
+    * each table's gradient is summed over the ranks — a dense all_reduce when the table is smaller than the rows
+      that would have to travel (FB15k-237 / WN18RR-size entity tables, all relation tables), otherwise the sparse
+      (row id, row) exchange of ``exchange_sparse_rows`` (4M-entity table) —
+    * and the row-sparse Adagrad step runs on the union of the touched rows, identically on every rank.
+
+    Local gradients are pre-scaled by 1/world, so the summed gradient is the gradient of the global mean loss."""
+
+    def __init__(self, *args, process_group=None, **kw):
+        super().__init__(*args, **kw)
+        self.pg = process_group
+        self.world = _world(process_group)
+        self.rank_id = dist.get_rank(process_group) if self.world > 1 else 0
+        self.grad_scale = 1.0 / self.world
+        self.local_batch_size = self.batch_size // self.world      # batch_size is the GLOBAL batch
+        if not (self.fused and self.sparse_adagrad):
+            raise ValueError("FusedDataParallelKGOptimizer needs torch.optim.Adagrad (lr_decay=0, weight_decay=0), a zero "
+                             "regulariser weight and update_steps=1; use DataParallelKGOptimizer otherwise")
+
+    def _step_body(self, batch):                     # graph-captured part: local forward/backward only
+        self._touched = self._forward_backward(batch)
+
+    def _gather(self, t):
+        out = torch.empty((self.world * t.numel(),), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, t.reshape(-1).contiguous(), group=self.pg)
+        return out
+
+    def _post_step(self):
+        m, opt = self.model, self.optimizer
+        heads, rels, tails = self._touched
+        if self.world > 1:
+            heads_all, rels_all, tails_all = self._gather(heads), self._gather(rels), self._gather(tails)
+        else:
+            heads_all, rels_all, tails_all = heads, rels, tails.reshape(-1)
+        ent_rows = torch.cat([heads_all, tails_all])
+        zero_row = torch.zeros(1, dtype=torch.int64, device=heads.device)
+        plan = [(m.entity.weight, ent_rows, torch.cat([heads, tails.reshape(-1)])), (m.rel.weight, rels_all, rels),
+                (m.rel_diag.weight, rels_all, rels), (m.c.weight, rels_all if m.multi_c else zero_row, rels if m.multi_c else zero_row)]
+        if m._ctx_weight() is not None:
+            plan.append((m._ctx_weight(), rels_all, rels))
+        if m.bias == "learn":
+            plan += [(m.bh.weight, heads_all, heads), (m.bt.weight, tails_all, tails.reshape(-1))]
+        if self.world > 1:
+            for p, rows_all, rows_local in plan:
+                row_bytes = (p.shape[1] if p.dim() > 1 else 1) * p.element_size() + 8
+                if p.numel() * p.element_size() <= rows_local.numel() * row_bytes * self.world:
+                    dist.all_reduce(p.grad, op=dist.ReduceOp.SUM, group=self.pg)          # small table: dense sum
+                else:
+                    exchange_sparse_rows(p.grad, rows_local, self.pg)                     # big table: only touched rows travel
+                    p.grad.mul_(self.world)                                               # (it averages; we pre-scaled by 1/world)
+        lr, eps = opt.param_groups[0]["lr"], opt.param_groups[0]["eps"]
+        ops.multi_sparse_adagrad([dict(param=p.data, grad=p.grad, state_sum=opt.state[p]["sum"], rows=rows_all.contiguous(),
+                                       stamp=self._stamps[p]) for p, rows_all, _ in plan], lr, eps, self._step_id)
+        ops.step_counter_bump(self._step_id)
+        for p in m.parameters():
+            opt.state[p]["step"] += 1
+
+    def step(self, global_batch):
+        self.fused_step(global_batch[self.rank_id::self.world].to(self.device))

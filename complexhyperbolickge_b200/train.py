@@ -39,6 +39,8 @@ class FusedKGOptimizer(KGOptimizer):
         self._loss_sum = torch.zeros((), dtype=m.entity.weight.dtype, device=dev)
         self._step_id = torch.ones((), dtype=torch.int32, device=dev)
         self._stamps = {}
+        self.local_batch_size = self.batch_size      # data parallel: batch_size / world
+        self.grad_scale = 1.0                        # data parallel: 1/world (mean over ranks of the local mean losses)
         if self.fused:
             for p in m.parameters():                 # static dense gradient buffers, all-zero between steps
                 if p.grad is None:
@@ -64,20 +66,22 @@ class FusedKGOptimizer(KGOptimizer):
             scores = ops.score_gather_fwd(r, B, nt, q, 1, 0, ent, tails, 0, bh_vals, 1 if learn else 0, 0,
                                           m.bt.weight.view(-1) if learn else None)
             gs = ops.nsloss(scores, self._loss_sum)
+            if self.grad_scale != 1.0:
+                gs.mul_(self.grad_scale)
             grad_q = ops.score_gather_bwd_scatter(r, B, nt, q, 1, 0, ent, tails, gs, ent.grad)
             g_ent, g_rel, g_rd, g_ctx, g_c = ops.query_bwd(m.KIND, r, bool(m.multi_c), ent, rel, rd, ctx, cw, heads, rels, grad_q)
-            ops.scatter_add_rows(ent.grad, heads, g_ent)
-            ops.scatter_add_rows(rel.grad, rels, g_rel)
-            ops.scatter_add_rows(rd.grad, rels, g_rd)
+            tabs = [dict(grad=ent.grad, rows=heads, src_rows=g_ent), dict(grad=rel.grad, rows=rels, src_rows=g_rel),
+                    dict(grad=rd.grad, rows=rels, src_rows=g_rd)]
             if ctx is not None:
-                ops.scatter_add_rows(ctx.grad, rels, g_ctx)
+                tabs.append(dict(grad=ctx.grad, rows=rels, src_rows=g_ctx))
             if m.multi_c:
-                ops.scatter_add_rows(cw.grad, rels, g_c)
+                tabs.append(dict(grad=cw.grad, rows=rels, src_rows=g_c))
             else:
                 cw.grad += g_c.sum()
             if learn:
-                ops.scatter_add_rows(m.bh.weight.grad, heads, gs.sum(1).contiguous())
-                ops.scatter_add_rows(m.bt.weight.grad, tails.view(-1), gs)
+                tabs.append(dict(grad=m.bh.weight.grad, rows=heads, src_rows=gs.sum(1).contiguous()))
+                tabs.append(dict(grad=m.bt.weight.grad, rows=tails.view(-1), src_rows=gs))
+            ops.multi_scatter_add(tabs)          # all row scatters of the step in one launch
         return heads, rels, tails
 
     def _sparse_step(self, heads, rels, tails):
@@ -91,8 +95,8 @@ class FusedKGOptimizer(KGOptimizer):
             plan.append((m._ctx_weight(), rels))
         if m.bias == "learn":
             plan += [(m.bh.weight, heads), (m.bt.weight, tails.view(-1))]
-        for p, rows in plan:
-            ops.sparse_adagrad(p.data, p.grad, opt.state[p]["sum"], rows.contiguous(), lr, eps, self._stamps[p], self._step_id)
+        ops.multi_sparse_adagrad([dict(param=p.data, grad=p.grad, state_sum=opt.state[p]["sum"], rows=rows.contiguous(),
+                                       stamp=self._stamps[p]) for p, rows in plan], lr, eps, self._step_id)
         ops.step_counter_bump(self._step_id)
 
     def _step_body(self, batch):
@@ -102,7 +106,7 @@ class FusedKGOptimizer(KGOptimizer):
 
     def fused_step(self, batch):
         """One training step on a device batch (B, 3); the loss is added to the device-side epoch accumulator."""
-        full = batch.shape[0] == self.batch_size
+        full = batch.shape[0] == self.local_batch_size
         if self.use_cuda_graph and full:
             if self._graph is None:
                 self._static_batch = batch.clone()

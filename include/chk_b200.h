@@ -100,6 +100,20 @@ int chk_nsloss(int dtype, int64_t B, int64_t nt, const void* scores, void* loss_
 int chk_sparse_adagrad(int dtype, void* param, void* grad, void* state_sum, const int64_t* rows, int64_t m,
                        int64_t width, double lr, double eps, int32_t* stamp, const int32_t* step_id, void* stream);
 int chk_step_counter_bump(int32_t* counter, void* stream);
+/* The same two operations over several tables in ONE launch each (entity, rel, rel_diag, context_vec, c, bh, bt):
+ *   chk_multi_scatter_add:     grad[rows[i], :] += src_rows[i, :]            (tables with src_rows == NULL are skipped)
+ *   chk_multi_sparse_adagrad:  the chk_sparse_adagrad update on rows[0..m) of every table. */
+#define CHK_MAX_TABLES 8
+typedef struct chk_table_desc {
+    void* param; void* grad; void* state_sum;   /* dense [n_rows, width] tensors (param / state_sum unused by the scatter) */
+    const int64_t* rows; int64_t m;             /* row ids touched in this step (duplicates allowed) */
+    const void* src_rows;                       /* scatter only: [m, width] rows to add */
+    int64_t width;
+    int32_t* stamp;                             /* adagrad only: int32 [n_rows] scratch */
+} chk_table_desc;
+int chk_multi_scatter_add(int dtype, const chk_table_desc* tabs, int n_tables, void* stream);
+int chk_multi_sparse_adagrad(int dtype, const chk_table_desc* tabs, int n_tables, double lr, double eps,
+                             const int32_t* step_id, void* stream);
 
 /* ---- K2: scoring against the whole entity table + filtered rank counts (evaluation) -------------
  * All K2 entry points share ONE canonical pair-score arithmetic (ascending-k FMA chain, see

@@ -80,6 +80,41 @@ def main():
             print(f"[dp step {name} r={r} {dtype} x{world}] loss single {l1.item():.9f} mean-of-ranks {lsum.item() / world:.9f}  "
                   f"max |param diff| / max|param| after one Adagrad step = {worst:.2e}", flush=True)
         assert abs(l1.item() - lsum.item() / world) < 1e-4 and worst < (1e-9 if dtype == "double" else 1e-4)
+        # ---- fused data-parallel step (CUDA graph + dense/sparse exchange + row-sparse Adagrad) vs single-GPU fused step
+        from complexhyperbolickge_b200.parallel import FusedDataParallelKGOptimizer
+        from complexhyperbolickge_b200.train import FusedKGOptimizer
+
+        class FixedF(FusedKGOptimizer):
+            def get_neg_samples(self, input_batch):
+                return self._negs_static
+
+        class FixedFDP(FusedDataParallelKGOptimizer):
+            def get_neg_samples(self, input_batch):
+                return self._negs_static
+
+        ref.load_state_dict(model.state_dict())
+        f1 = FixedF(ref, N3(0.0), torch.optim.Adagrad(ref.parameters(), lr=0.05), B, 1, neg, False, verbose=False)
+        f2 = FixedFDP(model, N3(0.0), torch.optim.Adagrad(model.parameters(), lr=0.05), B, 1, neg, False, verbose=False,
+                      process_group=dist.group.WORLD)
+        f1._negs_static = torch.zeros(B, neg, dtype=torch.int64, device=dev)
+        f2._negs_static = torch.zeros(B // world, neg, dtype=torch.int64, device=dev)
+        for it in range(4):
+            batch = torch.stack([torch.randint(0, n_ent, (B,), generator=g), torch.randint(0, n_rel2, (B,), generator=g),
+                                 torch.randint(0, n_ent, (B,), generator=g)], 1).to(dev)
+            negs = torch.randint(0, n_ent, (B, neg), generator=g).to(dev)
+            f1._negs_static.copy_(negs)
+            f2._negs_static.copy_(negs[rank::world])
+            f1.fused_step(batch)
+            f2.step(batch)
+        worst = 0.0
+        for (k, a), (_, b) in zip(ref.named_parameters(), model.named_parameters()):
+            worst = max(worst, (a.detach() - b.detach()).abs().max().item() / max(a.detach().abs().max().item(), 1e-30))
+        lsum = f2._loss_sum.clone().double()
+        dist.all_reduce(lsum)
+        if rank == 0:
+            print(f"[fused dp {name} r={r} {dtype} x{world}] 4 steps: loss single {f1._loss_sum.item() / 4:.9f} mean-of-ranks "
+                  f"{lsum.item() / world / 4:.9f}  max |param diff| / max|param| = {worst:.2e}", flush=True)
+        assert worst < (1e-9 if dtype == "double" else 2e-4)
         model.release_eval_cache()
     dist.barrier()
     if rank == 0:
