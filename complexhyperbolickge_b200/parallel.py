@@ -157,20 +157,36 @@ class FusedDataParallelKGOptimizer(FusedKGOptimizer):
         if not (self.fused and self.sparse_adagrad):
             raise ValueError("FusedDataParallelKGOptimizer needs torch.optim.Adagrad (lr_decay=0, weight_decay=0), a zero "
                              "regulariser weight and update_steps=1; use DataParallelKGOptimizer otherwise")
+        # Tables whose dense gradient is smaller than the rows that would have to travel are summed with ONE dense
+        # all_reduce: their .grad tensors are views into one flat buffer.  The others use the sparse row exchange.
+        rows_per_step = self.local_batch_size * (2 + self.neg_sample_size) * self.world
+        params = list(self.model.parameters())
+        self._dense = [p for p in params
+                       if p.numel() * p.element_size() <= rows_per_step * ((p.shape[1] if p.dim() > 1 else 1) * p.element_size() + 8)]
+        self._sparse = [p for p in params if not any(p is d for d in self._dense)]
+        if self._dense:
+            flat = torch.zeros(sum(p.numel() for p in self._dense), dtype=params[0].dtype, device=params[0].device)
+            o = 0
+            for p in self._dense:
+                p.grad = flat[o:o + p.numel()].view_as(p)
+                o += p.numel()
+            self._flat_grad = flat
 
     def _step_body(self, batch):                     # graph-captured part: local forward/backward only
         self._touched = self._forward_backward(batch)
 
-    def _gather(self, t):
-        out = torch.empty((self.world * t.numel(),), dtype=t.dtype, device=t.device)
-        dist.all_gather_into_tensor(out, t.reshape(-1).contiguous(), group=self.pg)
-        return out
-
     def _post_step(self):
         m, opt = self.model, self.optimizer
         heads, rels, tails = self._touched
-        if self.world > 1:
-            heads_all, rels_all, tails_all = self._gather(heads), self._gather(rels), self._gather(tails)
+        nb = heads.numel()
+        if self.world > 1:                           # one all_gather for every touched row id of every rank
+            ids = torch.cat([heads, rels, tails.reshape(-1)])
+            allids = torch.empty((self.world, ids.numel()), dtype=ids.dtype, device=ids.device)
+            dist.all_gather_into_tensor(allids, ids, group=self.pg)
+            heads_all, rels_all, tails_all = (allids[:, :nb].reshape(-1), allids[:, nb:2 * nb].reshape(-1),
+                                              allids[:, 2 * nb:].reshape(-1))
+            if self._dense:
+                dist.all_reduce(self._flat_grad, op=dist.ReduceOp.SUM, group=self.pg)
         else:
             heads_all, rels_all, tails_all = heads, rels, tails.reshape(-1)
         ent_rows = torch.cat([heads_all, tails_all])
@@ -182,11 +198,8 @@ class FusedDataParallelKGOptimizer(FusedKGOptimizer):
         if m.bias == "learn":
             plan += [(m.bh.weight, heads_all, heads), (m.bt.weight, tails_all, tails.reshape(-1))]
         if self.world > 1:
-            for p, rows_all, rows_local in plan:
-                row_bytes = (p.shape[1] if p.dim() > 1 else 1) * p.element_size() + 8
-                if p.numel() * p.element_size() <= rows_local.numel() * row_bytes * self.world:
-                    dist.all_reduce(p.grad, op=dist.ReduceOp.SUM, group=self.pg)          # small table: dense sum
-                else:
+            for p, _rows_all, rows_local in plan:
+                if any(p is s_ for s_ in self._sparse):
                     exchange_sparse_rows(p.grad, rows_local, self.pg)                     # big table: only touched rows travel
                     p.grad.mul_(self.world)                                               # (it averages; we pre-scaled by 1/world)
         lr, eps = opt.param_groups[0]["lr"], opt.param_groups[0]["eps"]
