@@ -122,12 +122,30 @@ __device__ __forceinline__ void dot_step(T zr, T zi, T wr, T wi, T& re, T& im) {
     im = Sc<T>::fma_(-zr, wi, im);
 }
 
+// ---- the canonical summation order ------------------------------------------------------------------
+// fp64: one ascending-k FMA chain.  fp32: BLOCKED — the chain restarts every CHK_BLK = 16 complex coefficients and the
+// block partials are added (separately rounded) in ascending order.  Every exact kernel (tile kernel, target,
+// filter pass, re-check) uses the same order, so their pair scores are bit-identical; the blocked order brings the
+// worst-case rounding bound of the fp32 dot from 2r units down to 2*16 + r/16 (514 -> 49 at rank 257), which is
+// what the tensor-core tier's error band (chk_rank_mma.cu) is built from.
+template <typename T> struct Chain { static constexpr int BLK = 0; };
+template <> struct Chain<float> { static constexpr int BLK = 16; };
+
 // ---- exact per-pair score (canonical chain, one thread per pair) -----------------------------------
 template <typename T>
 __device__ __forceinline__ T exact_pair(const T* __restrict__ z, const T* __restrict__ w, int r, T zn, T wn,
                                         bool has_bias, T bh, T bt) {
     T re = T(0), im = T(0);
-    for (int k = 0; k < r; ++k) dot_step<T>(z[k], z[r + k], w[k], w[r + k], re, im);
+    if (Chain<T>::BLK == 0) {
+        for (int k = 0; k < r; ++k) dot_step<T>(z[k], z[r + k], w[k], w[r + k], re, im);
+    } else {
+        for (int k0 = 0; k0 < r; k0 += Chain<T>::BLK) {
+            T pr = T(0), pi = T(0);
+            const int k1 = min(k0 + Chain<T>::BLK, r);
+            for (int k = k0; k < k1; ++k) dot_step<T>(z[k], z[r + k], w[k], w[r + k], pr, pi);
+            re = Sc<T>::add_(re, pr); im = Sc<T>::add_(im, pi);
+        }
+    }
     return pair_score<T>(re, im, zn, wn, has_bias, bh, bt);
 }
 
@@ -182,8 +200,18 @@ __device__ __forceinline__ T warp_exact_pairs(const RArgs<T>& A, unsigned i, uns
         }
         cp_async_wait_all();
         __syncwarp();
-        if (valid)
-            for (int kk = 0; kk < kc; ++kk) dot_step<T>(S.zr[lane][kk], S.zi[lane][kk], S.wr[lane][kk], S.wi[lane][kk], re, im);
+        if (valid) {
+            if (Chain<T>::BLK == 0) {
+                for (int kk = 0; kk < kc; ++kk) dot_step<T>(S.zr[lane][kk], S.zi[lane][kk], S.wr[lane][kk], S.wi[lane][kk], re, im);
+            } else {                                 // k0 is a multiple of 32: block boundaries fall at kk = 0, 16
+                for (int b0 = 0; b0 < kc; b0 += Chain<T>::BLK) {
+                    T pr = T(0), pi = T(0);
+                    const int b1 = min(b0 + Chain<T>::BLK, kc);
+                    for (int kk = b0; kk < b1; ++kk) dot_step<T>(S.zr[lane][kk], S.zi[lane][kk], S.wr[lane][kk], S.wi[lane][kk], pr, pi);
+                    re = Sc<T>::add_(re, pr); im = Sc<T>::add_(im, pi);
+                }
+            }
+        }
     }
     if (!valid) return T(0);
     const bool has_bias = A.bt != nullptr;

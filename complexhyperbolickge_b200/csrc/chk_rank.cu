@@ -51,7 +51,9 @@ __global__ void __launch_bounds__(256) rank_tile_kernel(RArgs<T> A) {
     const int64_t q0 = (int64_t)blockIdx.x * BQ;
     const int64_t e0 = (int64_t)blockIdx.y * BE;
 
-    T re[TQ][TE], im[TQ][TE];
+    static_assert(Chain<T>::BLK == 0 || Chain<T>::BLK == KC, "the K chunk is the canonical summation block");
+    constexpr bool BLOCKED = Chain<T>::BLK != 0;
+    T re[TQ][TE], im[TQ][TE];                      // running totals
 #pragma unroll
     for (int i = 0; i < TQ; ++i)
 #pragma unroll
@@ -79,31 +81,43 @@ __global__ void __launch_bounds__(256) rank_tile_kernel(RArgs<T> A) {
             sE[1][kk][row] = ok ? p[r] : T(0);
         }
         __syncthreads();
+        // fp32: this chunk's partial sums start from zero and are added to the totals afterwards (blocked canonical
+        // order); fp64: the chunk continues the single chain in the totals.
+        T pre[BLOCKED ? TQ : 1][BLOCKED ? TE : 1], pim[BLOCKED ? TQ : 1][BLOCKED ? TE : 1];
+        if (BLOCKED) {
+#pragma unroll
+            for (int i = 0; i < TQ; ++i)
+#pragma unroll
+                for (int j = 0; j < TE; ++j) { pre[BLOCKED ? i : 0][BLOCKED ? j : 0] = T(0); pim[BLOCKED ? i : 0][BLOCKED ? j : 0] = T(0); }
+        }
+        auto kstep = [&](int kk) {
+            T zr[TQ], zi[TQ], wr[TE], wi[TE];
+#pragma unroll
+            for (int i = 0; i < TQ; ++i) { zr[i] = sQ[0][kk][tq * TQ + i]; zi[i] = sQ[1][kk][tq * TQ + i]; }
+#pragma unroll
+            for (int j = 0; j < TE; ++j) { wr[j] = sE[0][kk][te * TE + j]; wi[j] = sE[1][kk][te * TE + j]; }
+#pragma unroll
+            for (int i = 0; i < TQ; ++i)
+#pragma unroll
+                for (int j = 0; j < TE; ++j) {
+                    if (BLOCKED) dot_step<T>(zr[i], zi[i], wr[j], wi[j], pre[BLOCKED ? i : 0][BLOCKED ? j : 0], pim[BLOCKED ? i : 0][BLOCKED ? j : 0]);
+                    else dot_step<T>(zr[i], zi[i], wr[j], wi[j], re[i][j], im[i][j]);
+                }
+        };
         if (kc == KC) {
 #pragma unroll
-            for (int kk = 0; kk < KC; ++kk) {
-                T zr[TQ], zi[TQ], wr[TE], wi[TE];
-#pragma unroll
-                for (int i = 0; i < TQ; ++i) { zr[i] = sQ[0][kk][tq * TQ + i]; zi[i] = sQ[1][kk][tq * TQ + i]; }
-#pragma unroll
-                for (int j = 0; j < TE; ++j) { wr[j] = sE[0][kk][te * TE + j]; wi[j] = sE[1][kk][te * TE + j]; }
-#pragma unroll
-                for (int i = 0; i < TQ; ++i)
-#pragma unroll
-                    for (int j = 0; j < TE; ++j) dot_step<T>(zr[i], zi[i], wr[j], wi[j], re[i][j], im[i][j]);
-            }
+            for (int kk = 0; kk < KC; ++kk) kstep(kk);
         } else {
-            for (int kk = 0; kk < kc; ++kk) {
-                T zr[TQ], zi[TQ], wr[TE], wi[TE];
+            for (int kk = 0; kk < kc; ++kk) kstep(kk);
+        }
+        if (BLOCKED) {
 #pragma unroll
-                for (int i = 0; i < TQ; ++i) { zr[i] = sQ[0][kk][tq * TQ + i]; zi[i] = sQ[1][kk][tq * TQ + i]; }
+            for (int i = 0; i < TQ; ++i)
 #pragma unroll
-                for (int j = 0; j < TE; ++j) { wr[j] = sE[0][kk][te * TE + j]; wi[j] = sE[1][kk][te * TE + j]; }
-#pragma unroll
-                for (int i = 0; i < TQ; ++i)
-#pragma unroll
-                    for (int j = 0; j < TE; ++j) dot_step<T>(zr[i], zi[i], wr[j], wi[j], re[i][j], im[i][j]);
-            }
+                for (int j = 0; j < TE; ++j) {
+                    re[i][j] = Sc<T>::add_(re[i][j], pre[BLOCKED ? i : 0][BLOCKED ? j : 0]);
+                    im[i][j] = Sc<T>::add_(im[i][j], pim[BLOCKED ? i : 0][BLOCKED ? j : 0]);
+                }
         }
     }
     // ---- fused epilogue ----

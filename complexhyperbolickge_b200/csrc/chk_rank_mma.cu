@@ -703,14 +703,16 @@ static int rank_mma_launch(int rank, int64_t b, const void* q, const void* qn, c
     const uint8_t* a_blocks = (const uint8_t*)shadow;
     const float4* aux = (const float4*)(a_blocks + n_et_pad * nk * (int64_t)A_BLOCK);
     // Bound on |re~ - re_exact| (and im) relative to ||z|| ||w|| >= sum_k |z_k||w_k| (Cauchy-Schwarz):
-    //   exact tier's canonical chain: 2r fused steps, each <= 2^-24 relative (standard recursive-summation bound);
+    //   exact tier's canonical BLOCKED chain (chk_common.cuh Chain<float>): 2*16 fused steps per block + r/16 block adds,
+    //   each <= 2^-24 relative (standard recursive-summation bound);
     //   bf16 split: |a - hi - lo| <= 2^-18 |a| per operand plus the dropped lo*lo term -> 3 * 2^-18, rounded up to 2^-16;
     //   tensor-core accumulation (hardware model, stated in DESIGN.md): every tcgen05.mma K=16 step adds its 16
     //   exact products to the fp32 accumulator with at most 2 units of 2^-23 relative to the largest magnitude
     //   involved (<= sum_k |a_k b_k|); 3 * Kpad/16 steps per accumulator.
     // tests/test_gpu_mma.py checks the observed |s~ - s| against the resulting band (it uses < 5 % of it).
     //   the Nyquist coefficient's four fp32 FMAs in the epilogue: 4 * 2^-24.
-    const double eps_dot = (2.0 * rank + 4.0) * 5.9604644775390625e-8 + 1.52587890625e-5 +
+    const double chain_steps = 2.0 * Chain<float>::BLK + (rank + Chain<float>::BLK - 1) / Chain<float>::BLK;
+    const double eps_dot = (chain_steps + 4.0) * 5.9604644775390625e-8 + 1.52587890625e-5 +
                            2.0 * (3.0 * nk * KC / 16.0) * 1.1920928955078125e-7;
     for (int64_t b0 = 0; b0 < b; b0 += MAX_B) {
         const int bc = (int)((b - b0) < MAX_B ? (b - b0) : MAX_B);

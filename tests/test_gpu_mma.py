@@ -131,3 +131,55 @@ def test_mma_overflow_flag_and_fallback(monkeypatch):
                     torch.zeros(1, dtype=torch.int64, device="cuda"), 0, counts, ops.entity_shadow(33, ent), ws)
     n_list, overflow = ops.rank_mma_status(ws)
     assert overflow and n_list > 1024
+
+
+def test_full_size_big4m_properties():
+    """BASELINE.json configs[4] at its FULL size (4,000,000 entities, rank 257): size-independent properties —
+    tensor-core counts == exact-tier counts, shard sums == single pass, counts bounded by the table size and
+    >= 1 without a filter (the target outranks itself), filtered count = unfiltered - #filtered hits."""
+    from complexhyperbolickge_b200 import ops
+    rank, n_ent, b = 257, 4_000_000, 40
+    g = torch.Generator(device="cuda").manual_seed(3)
+    std = float(np.sqrt(0.4 / (2 * rank)))
+    ent = torch.randn(n_ent, 2 * rank, generator=g, device="cuda") * std
+    q = torch.randn(b, 2 * rank, generator=g, device="cuda") * std
+    bh = torch.randn(b, generator=g, device="cuda") * 0.1
+    bt = torch.randn(n_ent, generator=g, device="cuda") * 0.1
+    tails = torch.randint(0, n_ent, (b,), generator=g, device="cuda")
+    qn, hn = ops.row_hnorm(rank, q), ops.row_hnorm(rank, ent)
+    rows = ent[tails].contiguous()
+    tgt = ops.target_scores(rank, q, qn, bh, rows, ops.row_hnorm(rank, rows), bt[tails].contiguous())
+    empty_ip = torch.zeros(b + 1, dtype=torch.int64, device="cuda")
+    dummy = torch.zeros(1, dtype=torch.int64, device="cuda")
+    c_fma = torch.zeros(b, dtype=torch.int64, device="cuda")
+    ops.rank_counts(ops.CHK_RANK_FMA, rank, q, qn, bh, tgt, ent, hn, bt, 0, empty_ip, dummy, 0, c_fma)
+    shadow = ops.entity_shadow(rank, ent)
+    ws = ops.rank_mma_workspace(rank, b, ent.device)
+    c_mma = torch.zeros(b, dtype=torch.int64, device="cuda")
+    ops.rank_counts(ops.CHK_RANK_MMA, rank, q, qn, bh, tgt, ent, hn, bt, 0, empty_ip, dummy, 0, c_mma, shadow, ws)
+    assert not ops.rank_mma_status(ws)[1]
+    assert torch.equal(c_mma, c_fma)
+    assert (c_fma >= 1).all() and (c_fma <= n_ent).all()
+    del shadow
+    # three contiguous shards (tile aligned) sum to the single pass
+    c_sh = torch.zeros(b, dtype=torch.int64, device="cuda")
+    bounds = [0, 1_333_376, 2_666_752, n_ent]
+    for lo, hi in zip(bounds[:-1], bounds[1:]):
+        e_s, h_s, b_s = ent[lo:hi], hn[lo:hi], bt[lo:hi]
+        sh = ops.entity_shadow(rank, e_s)
+        ops.rank_counts(ops.CHK_RANK_MMA, rank, q, qn, bh, tgt, e_s, h_s, b_s, lo, empty_ip, dummy, 0, c_sh, sh, ws)
+        del sh
+    assert torch.equal(c_sh, c_fma)
+    # filter = {target} U 5 random ids per query: filtered count = unfiltered - #{listed ids scoring >= target}
+    extra = torch.randint(0, n_ent, (b, 5), generator=g, device="cuda")
+    lists = [torch.unique(torch.cat([tails[i:i + 1], extra[i]])) for i in range(b)]
+    ip = torch.tensor([0] + list(np.cumsum([len(x) for x in lists])), dtype=torch.int64, device="cuda")
+    ix = torch.cat(lists).contiguous()
+    c_f = torch.zeros(b, dtype=torch.int64, device="cuda")
+    ops.rank_counts(ops.CHK_RANK_FMA, rank, q, qn, bh, tgt, ent, hn, bt, 0, ip, ix, ix.numel(), c_f)
+    want = c_fma.clone()
+    for i in range(b):
+        s_i = ops.score_all(rank, q[i:i + 1].contiguous(), qn[i:i + 1].contiguous(), bh[i:i + 1].contiguous(),
+                            ent[lists[i]].contiguous(), hn[lists[i]].contiguous(), bt[lists[i]].contiguous())
+        want[i] -= int((s_i[0] >= tgt[i]).sum())
+    assert torch.equal(c_f, want)
