@@ -172,10 +172,20 @@ class FusedDataParallelKGOptimizer(FusedKGOptimizer):
                 o += p.numel()
             self._flat_grad = flat
 
-    def _step_body(self, batch):                     # graph-captured part: local forward/backward only
+    def _step_body(self, batch):
+        """Local forward/backward, then — when every table takes the dense path (no host sync anywhere) — the
+        collectives and the optimizer too, so that the CUDA graph holds the whole step including the two NCCL calls."""
         self._touched = self._forward_backward(batch)
+        if not self._sparse:
+            self._exchange_and_update()
 
     def _post_step(self):
+        if self._sparse:
+            self._exchange_and_update()
+        for p in self.model.parameters():
+            self.optimizer.state[p]["step"] += 1
+
+    def _exchange_and_update(self):
         m, opt = self.model, self.optimizer
         heads, rels, tails = self._touched
         nb = heads.numel()
@@ -206,8 +216,6 @@ class FusedDataParallelKGOptimizer(FusedKGOptimizer):
         ops.multi_sparse_adagrad([dict(param=p.data, grad=p.grad, state_sum=opt.state[p]["sum"], rows=rows_all.contiguous(),
                                        stamp=self._stamps[p]) for p, rows_all, _ in plan], lr, eps, self._step_id)
         ops.step_counter_bump(self._step_id)
-        for p in m.parameters():
-            opt.state[p]["step"] += 1
 
     def step(self, global_batch):
         self.fused_step(global_batch[self.rank_id::self.world].to(self.device))
