@@ -337,7 +337,7 @@ def run_ours(args):
     model.eval()
     algo = args.rank_algo
     if algo == "auto":
-        algo = "mma" if (args.dtype == "float" and ops.mma_available()) else "fma"
+        algo = "mma" if ops.mma_available() else "fma"
     model.rank_algo = algo
     model.process_group = pg
     cfg["rank_algo"] = algo

@@ -47,11 +47,11 @@ SIGNATURES = {
     "chk_rank_counts": (_i, [_i, _i, _i, _i64, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _p, _p, _i64, _p, _p, _i64,
                              _p, _p]),
     "chk_entity_shadow_bytes": (_i64, [_i, _i64]),
-    "chk_entity_shadow_build": (_i, [_i, _i64, _p, _p, _p]),
+    "chk_entity_shadow_build": (_i, [_i, _i, _i64, _p, _p, _p, _p, _p]),
     "chk_rank_mma_workspace_bytes": (_i64, [_i, _i64]),
     "chk_rank_mma_reset": (_i, [_p, _p]),
     "chk_rank_mma_status": (_i, [_p, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int), _p]),
-    "chk_score_all_mma": (_i, [_i, _i64, _p, _p, _p, _p, _p, _p, _p, _i64, _p, _p, _i64, _p, _p, _p, _p]),
+    "chk_score_all_mma": (_i, [_i, _i, _i64, _p, _p, _p, _p, _p, _p, _p, _i64, _p, _p, _i64, _p, _p, _p, _p]),
 }
 
 _lib = None

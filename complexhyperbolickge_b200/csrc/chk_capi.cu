@@ -19,12 +19,12 @@ int chk_filter_subtract(int dtype, int rank, int64_t b, const void* q, const voi
                         const void* target, const void* entity, const void* hn, const void* bt,
                         int64_t n_rows, int64_t shard_offset, const int64_t* indptr, const int64_t* fidx,
                         int64_t total, int64_t* counts, cudaStream_t st);
-int chk_rank_counts_mma(int rank, int64_t b, const void* q, const void* qn, const void* bh_vals,
+int chk_rank_counts_mma(int dtype, int rank, int64_t b, const void* q, const void* qn, const void* bh_vals,
                         const void* target, const void* entity, const void* hn, const void* bt,
                         int64_t n_rows, const void* shadow, void* workspace, int64_t workspace_bytes,
                         int64_t* counts, cudaStream_t st);
 
-extern "C" int chk_abi_version(void) { return 1; }
+extern "C" int chk_abi_version(void) { return 2; }
 extern "C" const char* chk_last_error(void) { return g_err; }
 
 extern "C" int chk_rank_counts(int algo, int dtype, int rank, int64_t b, const void* q, const void* qn,
@@ -44,9 +44,8 @@ extern "C" int chk_rank_counts(int algo, int dtype, int rank, int64_t b, const v
     if (algo == CHK_RANK_FMA) {
         rc = chk_rank_counts_fma(dtype, rank, b, q, qn, bh_vals, target, entity, hn, bt, n_rows, counts, st);
     } else if (algo == CHK_RANK_MMA) {
-        if (dtype != CHK_F32) { chk_set_error("CHK_RANK_MMA is fp32 only (tcgen05 has no f64 kind)"); return CHK_EUNSUPPORTED; }
         if (!shadow || !workspace) { chk_set_error("CHK_RANK_MMA needs shadow and workspace"); return CHK_EINVAL; }
-        rc = chk_rank_counts_mma(rank, b, q, qn, bh_vals, target, entity, hn, bt, n_rows, shadow, workspace,
+        rc = chk_rank_counts_mma(dtype, rank, b, q, qn, bh_vals, target, entity, hn, bt, n_rows, shadow, workspace,
                                  workspace_bytes, counts, st);
     } else {
         chk_set_error("unknown rank algorithm %d", algo);

@@ -162,11 +162,19 @@ __device__ __forceinline__ void split_bf16(float a, __nv_bfloat16& hi, __nv_bflo
     hi = __float2bfloat16_rn(a);
     lo = __float2bfloat16_rn(a - __bfloat162float(hi));
 }
+__device__ __forceinline__ void split_bf16(double a, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+    hi = __double2bfloat16(a);                                   // round-to-nearest
+    lo = __double2bfloat16(a - (double)__bfloat162float(hi));    // residual formed in fp64: |a - hi - lo| <= 2^-18 |a|
+}
 
-// entity fp32 [n_rows, 2r] -> blocks[(et*nk + kc)] = { hi part | lo part } + aux[e] = { ||w_e|| (rounded up), Re w_{r-1}, Im w_{r-1}, 0 }
-__global__ void __launch_bounds__(256) entity_shadow_kernel(const float* __restrict__ entity, int64_t n_rows, int r, int nk,
-                                                            uint8_t* __restrict__ blocks, float4* __restrict__ aux) {
-    __shared__ float sT[TILE_E][KC + 1];
+// entity [n_rows, 2r] (fp32 or fp64) -> blocks[(et*nk + kc)] = { hi part | lo part },
+// aux[e] = { ||w_e|| (rounded up), Re w_{r-1}, Im w_{r-1}, 1/hn_e } and bt32[e] = (float) bt_e  (all fp32: epilogue inputs)
+template <typename TIn>
+__global__ void __launch_bounds__(256) entity_shadow_kernel(const TIn* __restrict__ entity, const TIn* __restrict__ hn,
+                                                            const TIn* __restrict__ bt, int64_t n_rows, int r, int nk,
+                                                            uint8_t* __restrict__ blocks, float4* __restrict__ aux,
+                                                            float* __restrict__ bt32) {
+    __shared__ TIn sT[TILE_E][KC + 1];
     __shared__ float sSq[TILE_E][4];
     const int64_t et = blockIdx.x;
     const int tid = threadIdx.x;
@@ -178,7 +186,7 @@ __global__ void __launch_bounds__(256) entity_shadow_kernel(const float* __restr
             int row = idx / KC, kk = idx - row * KC;
             int64_t e = et * TILE_E + row;
             int k = src_col(r, kc * KC + kk);
-            sT[row][kk] = (e < n_rows && k >= 0) ? entity[e * K2 + k] : 0.f;
+            sT[row][kk] = (e < n_rows && k >= 0) ? entity[e * K2 + k] : TIn(0);
         }
         __syncthreads();
         uint8_t* blk = blocks + ((size_t)et * nk + kc) * A_BLOCK;
@@ -189,9 +197,9 @@ __global__ void __launch_bounds__(256) entity_shadow_kernel(const float* __restr
             __align__(16) __nv_bfloat16 h[8], l[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                float a = sT[row][kcore * 8 + j];
+                const TIn a = sT[row][kcore * 8 + j];
                 split_bf16(a, h[j], l[j]);
-                sq[it] = fmaf(a, a, sq[it]);
+                sq[it] = fmaf((float)a, (float)a, sq[it]);
             }
             int off = tile_off(TILE_E, row, kcore * 8);
             *reinterpret_cast<uint4*>(blk + off) = *reinterpret_cast<const uint4*>(h);
@@ -204,15 +212,17 @@ __global__ void __launch_bounds__(256) entity_shadow_kernel(const float* __restr
     if (tid < TILE_E) {
         float s = (sSq[tid][0] + sSq[tid][1]) + (sSq[tid][2] + sSq[tid][3]);
         const int64_t e = et * TILE_E + tid;
-        const float wrn = e < n_rows ? entity[e * K2 + r - 1] : 0.f, win = e < n_rows ? entity[e * K2 + 2 * r - 1] : 0.f;
+        const float wrn = e < n_rows ? (float)entity[e * K2 + r - 1] : 0.f, win = e < n_rows ? (float)entity[e * K2 + 2 * r - 1] : 0.f;
         s = fmaf(wrn, wrn, fmaf(win, win, s));
-        aux[e] = make_float4(sqrtf(s) * (1.0f + 1e-6f), wrn, win, 0.f);
+        aux[e] = make_float4(sqrtf(s) * (1.0f + 1e-5f), wrn, win, e < n_rows ? (float)(TIn(1) / hn[e]) : -1.0f);
+        bt32[e] = e < n_rows ? (bt ? (float)bt[e] : 0.f) : -1e30f;      // padding rows can never reach a target
     }
 }
 
 // q fp32 [b, 2r] -> query blocks[(qt*nk + kc)] (rows 2i: [Re|Im], rows 2i+1: [Im|-Re]); grid (nk, n_qt), 256 threads
 // pair_layout: the block is two 128-row halves {hi | lo}{hi | lo} (one per CTA of a pair) instead of {hi | lo} of 256 rows
-__global__ void __launch_bounds__(256) query_blocks_kernel(const float* __restrict__ q, int b, int r, int nk, int pair_layout,
+template <typename TIn>
+__global__ void __launch_bounds__(256) query_blocks_kernel(const TIn* __restrict__ q, int b, int r, int nk, int pair_layout,
                                                            uint8_t* __restrict__ blocks) {
     const int kc = blockIdx.x, qt = blockIdx.y;
     const int K2 = 2 * r;
@@ -225,9 +235,9 @@ __global__ void __launch_bounds__(256) query_blocks_kernel(const float* __restri
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int kp = kc * KC + kcore * 8 + j, hh = r - 1;
-            float a = 0.f;
+            TIn a = TIn(0);
             if (i < b && kp < 2 * hh) {
-                const float* z = q + (size_t)i * K2;      // re-row: [Re z | Im z], im-row: [Im z | -Re z]
+                const TIn* z = q + (size_t)i * K2;        // re-row: [Re z | Im z], im-row: [Im z | -Re z]
                 a = !im_row ? (kp < hh ? z[kp] : z[r + kp - hh]) : (kp < hh ? z[r + kp] : -z[kp - hh]);
             }
             split_bf16(a, h[j], l[j]);
@@ -241,21 +251,22 @@ __global__ void __launch_bounds__(256) query_blocks_kernel(const float* __restri
 }
 
 // per-query constants {2/zn, bh, target, ||z||} and the batch maxima of ||z|| and |bh| (hdr[1], hdr[2]).  One warp per query.
-__global__ void __launch_bounds__(256) query_consts_kernel(const float* __restrict__ q, const float* __restrict__ qn,
-                                                           const float* __restrict__ bh_vals, const float* __restrict__ target,
+template <typename TIn>
+__global__ void __launch_bounds__(256) query_consts_kernel(const TIn* __restrict__ q, const TIn* __restrict__ qn,
+                                                           const TIn* __restrict__ bh_vals, const TIn* __restrict__ target,
                                                            int b, int r, float4* __restrict__ qc, float2* __restrict__ qny,
                                                            unsigned* __restrict__ hdr) {
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (i >= b) return;
-    const float* z = q + (size_t)i * 2 * r;
+    const TIn* z = q + (size_t)i * 2 * r;
     float s = 0.f;
-    for (int k = lane; k < 2 * r; k += 32) s = fmaf(z[k], z[k], s);
+    for (int k = lane; k < 2 * r; k += 32) s = fmaf((float)z[k], (float)z[k], s);
     s = warp_sum<float>(s);
     if (lane == 0) {
-        const float nz = sqrtf(s) * (1.0f + 1e-6f), bh = bh_vals ? bh_vals[i] : 0.f;
-        qc[i] = make_float4(2.0f / qn[i], bh, target[i], nz);
-        qny[i] = make_float2(z[r - 1], z[2 * r - 1]);        // Nyquist coefficient of the query
+        const float nz = sqrtf(s) * (1.0f + 1e-5f), bh = bh_vals ? (float)bh_vals[i] : 0.f;
+        qc[i] = make_float4((float)(TIn(2) / qn[i]), bh, (float)target[i], nz);
+        qny[i] = make_float2((float)z[r - 1], (float)z[2 * r - 1]);        // Nyquist coefficient of the query
         atomicMax(hdr + 1, __float_as_uint(nz));            // non-negative floats order like their bit patterns
         atomicMax(hdr + 2, __float_as_uint(fabsf(bh)));
     }
@@ -265,7 +276,9 @@ __global__ void __launch_bounds__(256) query_consts_kernel(const float* __restri
 struct MmaArgs {
     const uint8_t* a_blocks; const float4* aux;        // entity shadow: operand blocks, {||w||, Re w_{r-1}, Im w_{r-1}}
     const uint8_t* b_blocks; const float4* qc; const float2* qny;   // per-call query operands
-    const float* hn; const float* bt;                  // entity side vectors (bt may be NULL)
+    const float* bt32;                                 // entity shadow: fp32 copy of bt (0 without bias, -1e30 on padding rows)
+    float xclamp;                                      // 1 + eps of the MODEL dtype (4e-3 fp32, 1e-5 fp64), as fp32
+    int exact_clamp;                                   // fp32 models: clamp-regime pairs are decided bit-exactly in the epilogue
     int64_t n_rows; int b, nk, n_et, n_qt;
     float eps_dot;                                     // |re~ - re_exact| <= eps_dot * ||z|| ||w|| (both tiers' errors)
     unsigned* hdr; uint2* list; unsigned list_cap;     // hdr[0] = list length, hdr[1..2] = max||z||, max|bh|, hdr[4] = overflow (sticky)
@@ -396,7 +409,8 @@ __global__ void __launch_bounds__(THREADS, 1) rank_mma_kernel(const MmaArgs A) {
         }
     }
     for (int i = threadIdx.x; i < MAX_B; i += THREADS) {
-        sQc[i] = i < A.b ? A.qc[i] : make_float4(-2.f, 0.f, __int_as_float(0x7f800000), 0.f);
+        // slots past the batch: a huge FINITE target (the band has a 2^-22 |target| term; inf would make it inf and list the pair)
+        sQc[i] = i < A.b ? A.qc[i] : make_float4(-2.f, 0.f, 3.0e38f, 0.f);
         sQny[i] = i < A.b ? A.qny[i] : make_float2(0.f, 0.f);
         sCnt[i] = 0;
     }
@@ -479,11 +493,11 @@ __global__ void __launch_bounds__(THREADS, 1) rank_mma_kernel(const MmaArgs A) {
         //   band = (2 rho + dx) dx + slop,  rho = acosh/sqrt(x^2-1) = ln2 l rsqrt(xc^2-1)   (|d rho/dx| <= 1/3).
         const int lq = warp & 3;                       // TMEM lane quarter this warp may read
         const int chalf = (warp - 4) >> 2;             // which 128 columns (64 queries) of the tile
-        const float xclamp = 1.0f + Sc<float>::ball_eps;
-        const float s_clamp = score_from_x<float>(xclamp, false, 0.f, 0.f);     // exact tier's -acosh(1+eps)^2
+        const float xclamp = A.xclamp;
+        const float s_clamp = score_from_x<float>(1.0f + Sc<float>::ball_eps, false, 0.f, 0.f);   // exact fp32 tier's -acosh(1+eps)^2
         const float eps = A.eps_dot;
         const float nz_max = __uint_as_float(A.hdr[1]), bh_max = __uint_as_float(A.hdr[2]);
-        constexpr float kx = 16.f * 5.9604645e-8f;     // relative roundoff of (x+1) in both tiers
+        constexpr float kx = 24.f * 5.9604645e-8f;     // relative roundoff of (x+1) in both tiers (incl. fp32 copies of fp64 inputs)
         constexpr float LN2 = 0.69314718f, LN2SQ = 0.48045301f;
         constexpr float k1 = (3.8146973e-6f + 4.7683716e-7f) * LN2SQ;          // (2^-18 + 2^-21) d^2: evaluation roundoff of d^2
         const uint32_t tbase = tmem_base + ((uint32_t)(lq * 32) << 16) + chalf * 128;
@@ -493,11 +507,12 @@ __global__ void __launch_bounds__(THREADS, 1) rank_mma_kernel(const MmaArgs A) {
             const int acc = it & 1; const uint32_t acc_phase = (it >> 1) & 1;
             const int64_t e = (int64_t)et * TILE_E + lq * 32 + lane;
             const bool e_ok = e < A.n_rows;
-            const float iwn = e_ok ? 1.0f / A.hn[e] : -1.0f;
-            // rows past the end of the shard get bt = -1e30: their score can never reach a target (and stays finite)
-            const float bte = e_ok ? (A.bt ? A.bt[e] : 0.f) : -1e30f;
-            const float4 ax = e_ok ? A.aux[e] : make_float4(0.f, 0.f, 0.f, 0.f);
-            const float nwe = ax.x, wrn = ax.y, win = ax.z;       // ||w||, Re / Im of the Nyquist coefficient
+            // the shadow is padded to whole tiles: rows past the end of the shard carry bt = -1e30 (their score can never
+            // reach a target and stays finite), zero operands and 1/hn = -1
+            const float4 ax = A.aux[e];
+            const float bte = A.bt32[e];
+            const float nwe = ax.x, wrn = ax.y, win = ax.z, iwn = ax.w;   // ||w||, Nyquist coefficient, 1/hn
+            (void)e_ok;
             // dm2 = [sqrt2 eps P (1 + 4.3 eps P) + kx] (1 + mod2) >= |mod2~ - mod2| + kx mod2, P = ||z|| ||w|| <= nz_max ||w||
             const float cae = 1.4142136f * eps * nwe * (1.0f + 4.3f * eps * nz_max * nwe);
             // additive part of the band: 2^-21 (lg2/rsqrt approximation at small d) + 2^-22 (xc^2-1 cancellation)
@@ -512,7 +527,7 @@ __global__ void __launch_bounds__(THREADS, 1) rank_mma_kernel(const MmaArgs A) {
                 unsigned m_sure = 0, m_hi = 0;
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    const float4 c = sQc[qbase + j];              // {2/zn, bh, target (+inf beyond b), ||z||}: broadcast
+                    const float4 c = sQc[qbase + j];              // {2/zn, bh, target (3e38 beyond b), ||z||}: broadcast
                     const float2 zn_ = sQny[qbase + j];           // coefficient r-1 is contracted here, not in the MMA
                     const float re = fmaf(zn_.x, wrn, fmaf(zn_.y, win, __uint_as_float(v[2 * j])));
                     const float im = fmaf(zn_.y, wrn, fmaf(-zn_.x, win, __uint_as_float(v[2 * j + 1])));
@@ -523,7 +538,7 @@ __global__ void __launch_bounds__(THREADS, 1) rank_mma_kernel(const MmaArgs A) {
                     const float gq = c.x * iwn;                   // 2/(zn wn) > 0
                     const float x = fmaf(gq, mod2, -1.0f);
                     const float dx = gq * dm2;                    // bound on |x~ - x_exact| (before the clamp)
-                    const bool clamped = (x + dx) <= xclamp;      // the exact tier's x is clamped for sure
+                    const bool clamped = A.exact_clamp && (x + dx) <= xclamp;     // the exact tier's x is clamped for sure
                     const float xc = fmaxf(x, xclamp);
                     const float t = fmaf(xc, xc, -1.0f);
                     const float rs = rsqrt_approx(t);
@@ -531,13 +546,13 @@ __global__ void __launch_bounds__(THREADS, 1) rank_mma_kernel(const MmaArgs A) {
                     const float a2 = fmaf(l * rs, 2.0f * LN2, dx);       // 2 rho + dx
                     const float l2 = l * l;
                     const float bias = __fadd_rn(c.y, bte);
-                    float band = fmaf(a2, dx, fmaf(k1, l2, slop0));
+                    float band = fmaf(a2, dx, fmaf(k1, l2, fmaf(2.3841858e-7f, fabsf(c.z), slop0)));   // + 2^-22 |target|
                     float s = fmaf(-LN2SQ, l2, bias);
                     if (clamped) { s = __fadd_rn(bias, s_clamp); band = 0.f; }
                     m_sure |= (s - band >= c.z) ? (1u << j) : 0u;             // certainly >= target
                     m_hi |= !(s + band < c.z) ? (1u << j) : 0u;               // possibly >= target (NaN -> re-check)
                     if (DEBUG) {
-                        if (e_ok && qbase + j < A.b) {
+                        if (e < A.n_rows && qbase + j < A.b) {
                             A.dbg_scores[(size_t)(qbase + j) * A.n_rows + e] = A.dump_raw ? re : s;
                             A.dbg_band[(size_t)(qbase + j) * A.n_rows + e] = A.dump_raw ? im : band;
                         }
@@ -590,17 +605,18 @@ __global__ void __launch_bounds__(THREADS, 1) rank_mma_kernel(const MmaArgs A) {
 
 // exact re-check of the pairs the epilogue could not decide (canonical chain -> same bits as the exact tier);
 // one lane per pair, rows staged with coalesced warp loads (warp_exact_pairs)
-constexpr int RECHECK_WARPS = 2;
-__global__ void __launch_bounds__(RECHECK_WARPS * 32) recheck_kernel(RArgs<float> A, const unsigned* __restrict__ hdr,
-                                                                     const uint2* __restrict__ list, unsigned cap) {
-    __shared__ PairTiles<float> S[RECHECK_WARPS];
+template <typename T>
+__global__ void __launch_bounds__((sizeof(T) == 4 ? 2 : 1) * 32) recheck_kernel(RArgs<T> A, const unsigned* __restrict__ hdr,
+                                                                                const uint2* __restrict__ list, unsigned cap) {
+    constexpr int WARPS = sizeof(T) == 4 ? 2 : 1;
+    __shared__ PairTiles<T> S[WARPS];
     const unsigned n = hdr[0] < cap ? hdr[0] : cap;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (unsigned t0 = (blockIdx.x * RECHECK_WARPS + warp) * 32; t0 < n; t0 += gridDim.x * RECHECK_WARPS * 32) {
+    for (unsigned t0 = (blockIdx.x * WARPS + warp) * 32; t0 < n; t0 += gridDim.x * WARPS * 32) {
         const unsigned t = t0 + lane;
         const bool valid = t < n;
         const uint2 p = valid ? list[t] : make_uint2(0u, 0u);
-        const float s = warp_exact_pairs<float>(A, p.x, p.y, valid, S[warp]);
+        const T s = warp_exact_pairs<T>(A, p.x, p.y, valid, S[warp]);
         if (valid && s >= A.target[p.x]) atomicAdd(A.counts + p.x, 1ull);
     }
 }
@@ -631,18 +647,23 @@ int g_num_sms = 0;
 extern "C" int64_t chk_entity_shadow_bytes(int rank, int64_t n_rows) {
     if (rank < 2 || n_rows <= 0) return 0;
     const int64_t n_et = ((n_rows + TILE_E - 1) / TILE_E + 1) / 2 * 2;       // padded to whole tile pairs
-    return n_et * (kpad_of(rank) / KC) * (int64_t)A_BLOCK + n_et * TILE_E * 16;
+    return n_et * (kpad_of(rank) / KC) * (int64_t)A_BLOCK + n_et * TILE_E * (16 + 4);      // blocks + aux (float4) + bt32
 }
 
-extern "C" int chk_entity_shadow_build(int rank, int64_t n_rows, const void* entity_f32, void* shadow, void* stream) {
+extern "C" int chk_entity_shadow_build(int dtype, int rank, int64_t n_rows, const void* entity, const void* hn, const void* bt,
+                                       void* shadow, void* stream) {
     if (n_rows == 0) return CHK_OK;
-    if (rank < 2 || n_rows < 0 || !entity_f32 || !shadow) { chk_set_error("chk_entity_shadow_build: bad argument"); return CHK_EINVAL; }
+    if (rank < 2 || n_rows < 0 || !entity || !hn || !shadow) { chk_set_error("chk_entity_shadow_build: bad argument"); return CHK_EINVAL; }
     const int64_t n_et = ((n_rows + TILE_E - 1) / TILE_E + 1) / 2 * 2;       // padded to whole tile pairs (zero rows)
     if (n_et > 0x7fffffff) { chk_set_error("chk_entity_shadow_build: shard too large"); return CHK_EUNSUPPORTED; }
     const int nk = kpad_of(rank) / KC;
     uint8_t* blocks = (uint8_t*)shadow;
     float4* aux = (float4*)(blocks + n_et * nk * (int64_t)A_BLOCK);
-    entity_shadow_kernel<<<(unsigned)n_et, 256, 0, (cudaStream_t)stream>>>((const float*)entity_f32, n_rows, rank, nk, blocks, aux);
+    float* bt32 = (float*)(aux + n_et * TILE_E);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == CHK_F32) entity_shadow_kernel<float><<<(unsigned)n_et, 256, 0, st>>>((const float*)entity, (const float*)hn, (const float*)bt, n_rows, rank, nk, blocks, aux, bt32);
+    else if (dtype == CHK_F64) entity_shadow_kernel<double><<<(unsigned)n_et, 256, 0, st>>>((const double*)entity, (const double*)hn, (const double*)bt, n_rows, rank, nk, blocks, aux, bt32);
+    else { chk_set_error("unknown dtype %d", dtype); return CHK_EINVAL; }
     CHK_CUDA_LAUNCH_CHECK("entity_shadow_kernel");
     return CHK_OK;
 }
@@ -674,7 +695,8 @@ extern "C" int chk_rank_mma_status(const void* workspace, int64_t* last_list_len
     return CHK_OK;
 }
 
-static int rank_mma_launch(int rank, int64_t b, const void* q, const void* qn, const void* bh_vals, const void* target,
+template <typename T>
+static int rank_mma_launch_t(int rank, int64_t b, const void* q, const void* qn, const void* bh_vals, const void* target,
                            const void* entity, const void* hn, const void* bt, int64_t n_rows, const void* shadow,
                            void* workspace, int64_t workspace_bytes, int64_t* counts, float* dbg_scores, float* dbg_band,
                            cudaStream_t st) {
@@ -711,24 +733,28 @@ static int rank_mma_launch(int rank, int64_t b, const void* q, const void* qn, c
     //   involved (<= sum_k |a_k b_k|); 3 * Kpad/16 steps per accumulator.
     // tests/test_gpu_mma.py checks the observed |s~ - s| against the resulting band (it uses < 5 % of it).
     //   the Nyquist coefficient's four fp32 FMAs in the epilogue: 4 * 2^-24.
-    const double chain_steps = 2.0 * Chain<float>::BLK + (rank + Chain<float>::BLK - 1) / Chain<float>::BLK;
+    // fp64 models: the exact tier is an fp64 chain (2r steps of 2^-53: nothing), the inputs of the epilogue are fp32
+    // copies (covered by kx and the |target| / |bias| terms of the slop).
+    const double chain_steps = sizeof(T) == 8 ? 0.0 : 2.0 * Chain<float>::BLK + (rank + Chain<float>::BLK - 1) / Chain<float>::BLK;
     const double eps_dot = (chain_steps + 4.0) * 5.9604644775390625e-8 + 1.52587890625e-5 +
                            2.0 * (3.0 * nk * KC / 16.0) * 1.1920928955078125e-7;
     for (int64_t b0 = 0; b0 < b; b0 += MAX_B) {
         const int bc = (int)((b - b0) < MAX_B ? (b - b0) : MAX_B);
         const int n_qt = (bc + TILE_Q - 1) / TILE_Q;
-        const float* qp = (const float*)q + b0 * 2 * rank;
-        const float* qnp = (const float*)qn + b0;
-        const float* bhp = bh_vals ? (const float*)bh_vals + b0 : nullptr;
-        const float* tp = (const float*)target + b0;
+        const T* qp = (const T*)q + b0 * 2 * rank;
+        const T* qnp = (const T*)qn + b0;
+        const T* bhp = bh_vals ? (const T*)bh_vals + b0 : nullptr;
+        const T* tp = (const T*)target + b0;
         if (cudaMemsetAsync(W.hdr, 0, 16, st) != cudaSuccess) { chk_set_error("cudaMemsetAsync failed"); return CHK_ECUDA; }
-        query_consts_kernel<<<(bc + 7) / 8, 256, 0, st>>>(qp, qnp, bhp, tp, bc, rank, W.qc, W.qny, W.hdr);
+        query_consts_kernel<T><<<(bc + 7) / 8, 256, 0, st>>>(qp, qnp, bhp, tp, bc, rank, W.qc, W.qny, W.hdr);
         CHK_CUDA_LAUNCH_CHECK("query_consts_kernel");
-        query_blocks_kernel<<<dim3(nk, n_qt), 256, 0, st>>>(qp, bc, rank, nk, pair ? 1 : 0, W.b_blocks);
+        query_blocks_kernel<T><<<dim3(nk, n_qt), 256, 0, st>>>(qp, bc, rank, nk, pair ? 1 : 0, W.b_blocks);
         CHK_CUDA_LAUNCH_CHECK("query_blocks_kernel");
         MmaArgs A{};
         A.a_blocks = a_blocks; A.aux = aux; A.b_blocks = W.b_blocks; A.qc = W.qc; A.qny = W.qny;
-        A.hn = (const float*)hn; A.bt = (const float*)bt; A.n_rows = n_rows; A.b = bc; A.nk = nk; A.n_et = (int)n_et; A.n_qt = n_qt;
+        A.bt32 = (const float*)(aux + n_et_pad * TILE_E);
+        A.xclamp = (float)(T(1) + Sc<T>::ball_eps); A.exact_clamp = sizeof(T) == 4 ? 1 : 0;
+        A.n_rows = n_rows; A.b = bc; A.nk = nk; A.n_et = (int)n_et; A.n_qt = n_qt;
         A.eps_dot = (float)eps_dot; A.hdr = W.hdr; A.list = W.list; A.list_cap = W.list_cap;
         A.counts = (unsigned long long*)counts + b0;
         { const char* dr = getenv("CHK_MMA_DUMP_RAW"); A.dump_raw = (dr && dr[0] == '1') ? 1 : 0; }
@@ -754,30 +780,39 @@ static int rank_mma_launch(int rank, int64_t b, const void* q, const void* qn, c
             else rank_mma_kernel<false, false><<<grid, THREADS, Geo<false>::SMEM, st>>>(A);
         }
         CHK_CUDA_LAUNCH_CHECK("rank_mma_kernel");
-        RArgs<float> R{};
-        R.q = qp; R.qn = qnp; R.bh_vals = bhp; R.target = tp; R.entity = (const float*)entity; R.hn = (const float*)hn;
-        R.bt = (const float*)bt; R.b = bc; R.n_rows = n_rows; R.r = rank; R.counts = (unsigned long long*)counts + b0;
-        recheck_kernel<<<g_num_sms * 6, RECHECK_WARPS * 32, 0, st>>>(R, W.hdr, W.list, W.list_cap);
+        RArgs<T> R{};
+        R.q = qp; R.qn = qnp; R.bh_vals = bhp; R.target = tp; R.entity = (const T*)entity; R.hn = (const T*)hn;
+        R.bt = (const T*)bt; R.b = bc; R.n_rows = n_rows; R.r = rank; R.counts = (unsigned long long*)counts + b0;
+        recheck_kernel<T><<<g_num_sms * 6, (sizeof(T) == 4 ? 2 : 1) * 32, 0, st>>>(R, W.hdr, W.list, W.list_cap);
         CHK_CUDA_LAUNCH_CHECK("recheck_kernel");
     }
     return CHK_OK;
 }
 
-int chk_rank_counts_mma(int rank, int64_t b, const void* q, const void* qn, const void* bh_vals,
+static int rank_mma_launch(int dtype, int rank, int64_t b, const void* q, const void* qn, const void* bh_vals, const void* target,
+                           const void* entity, const void* hn, const void* bt, int64_t n_rows, const void* shadow,
+                           void* workspace, int64_t workspace_bytes, int64_t* counts, float* dbg_scores, float* dbg_band,
+                           cudaStream_t st) {
+    if (dtype == CHK_F32) return rank_mma_launch_t<float>(rank, b, q, qn, bh_vals, target, entity, hn, bt, n_rows, shadow, workspace, workspace_bytes, counts, dbg_scores, dbg_band, st);
+    if (dtype == CHK_F64) return rank_mma_launch_t<double>(rank, b, q, qn, bh_vals, target, entity, hn, bt, n_rows, shadow, workspace, workspace_bytes, counts, dbg_scores, dbg_band, st);
+    chk_set_error("unknown dtype %d", dtype); return CHK_EINVAL;
+}
+
+int chk_rank_counts_mma(int dtype, int rank, int64_t b, const void* q, const void* qn, const void* bh_vals,
                         const void* target, const void* entity, const void* hn, const void* bt,
                         int64_t n_rows, const void* shadow, void* workspace, int64_t workspace_bytes,
                         int64_t* counts, cudaStream_t st) {
-    return rank_mma_launch(rank, b, q, qn, bh_vals, target, entity, hn, bt, n_rows, shadow, workspace, workspace_bytes,
+    return rank_mma_launch(dtype, rank, b, q, qn, bh_vals, target, entity, hn, bt, n_rows, shadow, workspace, workspace_bytes,
                            counts, nullptr, nullptr, st);
 }
 
-extern "C" int chk_score_all_mma(int rank, int64_t b, const void* q, const void* qn, const void* bh_vals,
+extern "C" int chk_score_all_mma(int dtype, int rank, int64_t b, const void* q, const void* qn, const void* bh_vals,
                                  const void* target, const void* entity, const void* hn, const void* bt, int64_t n_rows,
                                  const void* shadow, void* workspace, int64_t workspace_bytes, int64_t* counts,
                                  void* scores, void* band, void* stream) {
     if (b == 0 || n_rows == 0) return CHK_OK;
     if (b < 0 || n_rows < 0 || rank < 2 || !q || !qn || !target || !entity || !hn || !shadow || !workspace || !counts || !scores || !band ||
         ((bh_vals == nullptr) != (bt == nullptr))) { chk_set_error("chk_score_all_mma: bad argument"); return CHK_EINVAL; }
-    return rank_mma_launch(rank, b, q, qn, bh_vals, target, entity, hn, bt, n_rows, shadow, workspace, workspace_bytes,
+    return rank_mma_launch(dtype, rank, b, q, qn, bh_vals, target, entity, hn, bt, n_rows, shadow, workspace, workspace_bytes,
                            counts, (float*)scores, (float*)band, (cudaStream_t)stream);
 }

@@ -218,15 +218,17 @@ def rank_counts(algo, rank, q, qn, bh_vals, target, entity, hn, bt, shard_offset
     return counts
 
 
-def entity_shadow(rank, entity):
-    """bf16 hi/lo planes of an fp32 entity table for the tcgen05 tier (TMA-legal, K padded)."""
-    _chk(entity)
+def entity_shadow(rank, entity, hn=None, bt=None):
+    """Shadow of an entity shard for the tcgen05 tier: bf16 hi/lo operand blocks + fp32 epilogue inputs (fp32 or fp64 table)."""
+    _chk(entity, hn, bt)
+    if hn is None:
+        hn = row_hnorm(rank, entity)
     nbytes = _lib.lib().chk_entity_shadow_bytes(rank, entity.shape[0])
     if nbytes <= 0:
         raise RuntimeError("CHK_RANK_MMA shadow unavailable: " + _lib.lib().chk_last_error().decode())
     buf = torch.empty((nbytes,), dtype=torch.uint8, device=entity.device)
-    _lib.check(_lib.lib().chk_entity_shadow_build(rank, entity.shape[0], _p(entity), _p(buf), _stream()),
-               "chk_entity_shadow_build")
+    _lib.check(_lib.lib().chk_entity_shadow_build(_dt(entity), rank, entity.shape[0], _p(entity), _p(hn), _p(bt), _p(buf),
+                                                  _stream()), "chk_entity_shadow_build")
     _launched(1)
     return buf
 
@@ -267,7 +269,7 @@ def score_all_mma(rank, q, qn, bh_vals, target, entity, hn, bt, shadow, workspac
     scores = torch.full((b, n), float("nan"), dtype=torch.float32, device=q.device)
     band = torch.full((b, n), float("nan"), dtype=torch.float32, device=q.device)
     counts = torch.zeros((b,), dtype=torch.int64, device=q.device)
-    _lib.check(_lib.lib().chk_score_all_mma(rank, b, _p(q), _p(qn), _p(bh_vals), _p(target), _p(entity), _p(hn),
+    _lib.check(_lib.lib().chk_score_all_mma(_dt(q), rank, b, _p(q), _p(qn), _p(bh_vals), _p(target), _p(entity), _p(hn),
                                             _p(bt), n, _p(shadow), _p(workspace),
                                             workspace.numel() * workspace.element_size(), _p(counts), _p(scores),
                                             _p(band), _stream()), "chk_score_all_mma")

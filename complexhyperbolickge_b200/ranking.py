@@ -38,10 +38,8 @@ class EvalState:
         self.hn = ops.row_hnorm(model.rank, self.entity) if self.hi > self.lo else ent.new_empty(0)
         self.algo = ops.CHK_RANK_MMA if model.rank_algo == "mma" else ops.CHK_RANK_FMA
         self.shadow = None
-        if self.algo == ops.CHK_RANK_MMA:
-            if ent.dtype != torch.float32:
-                raise RuntimeError("rank_algo='mma' is fp32 only (tcgen05 has no f64 kind); use 'fma' for --dtype double")
-            self.shadow = ops.entity_shadow(model.rank, self.entity) if self.hi > self.lo else None
+        if self.algo == ops.CHK_RANK_MMA:       # fp32 and fp64 models: bf16x3 prefilter, exact re-check in the model dtype
+            self.shadow = ops.entity_shadow(model.rank, self.entity, self.hn, self.bt) if self.hi > self.lo else None
 
 
 def eval_state(model) -> EvalState:

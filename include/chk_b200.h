@@ -144,10 +144,11 @@ int chk_target_scores(int dtype, int rank, int64_t b, const void* q, const void*
  * filter_indptr[b].  Shard rows are global ids [shard_offset, shard_offset + n_rows).  counts is int64 [b],
  * accumulated (caller zeroes it); summing it over shards / GPUs gives rank - 1.
  * algo = CHK_RANK_FMA: exact fp32/fp64 FMA tiles.
- * algo = CHK_RANK_MMA (fp32 only): the contraction runs on tcgen05 (bf16x3 split, fp32 accumulation in TMEM) from
- *   the pre-tiled bf16 shadow of chk_entity_shadow_build; the epilogue decides every pair whose approximate
- *   score is outside a proven error band around the target, and the pairs inside the band are re-scored with
- *   the exact chain, so the counts EQUAL CHK_RANK_FMA's.  Needs `shadow` (built for the same entity/n_rows) and
+ * algo = CHK_RANK_MMA (fp32 AND fp64 models): the contraction runs on tcgen05 (bf16x3 split, fp32 accumulation in
+ *   TMEM) from the pre-tiled bf16 shadow of chk_entity_shadow_build; the epilogue decides every pair whose
+ *   approximate score is outside a proven error band around the target, and the pairs inside the band are
+ *   re-scored with the exact chain IN THE MODEL'S dtype, so the counts EQUAL CHK_RANK_FMA's (for --dtype double:
+ *   fp64-exact ranks at tensor-core speed; tcgen05 has no f64 kind, the fp64 work is only the re-check).  Needs `shadow` (built for the same entity/n_rows) and
  *   a workspace of chk_rank_mma_workspace_bytes(rank, b) bytes.  If the band list overflows, a sticky flag is
  *   raised in the workspace (read it with chk_rank_mma_status after the pass; the counts of that pass are then
  *   invalid and the caller re-runs it with CHK_RANK_FMA). */
@@ -158,7 +159,11 @@ int chk_rank_counts(int algo, int dtype, int rank, int64_t b, const void* q, con
                     const void* shadow, void* workspace, int64_t workspace_bytes,
                     int64_t* counts, void* stream);
 int64_t chk_entity_shadow_bytes(int rank, int64_t n_rows);
-int chk_entity_shadow_build(int rank, int64_t n_rows, const void* entity_f32, void* shadow, void* stream);
+/* Shadow of an entity shard for CHK_RANK_MMA: bf16 hi/lo operand blocks (pre-tiled for 1-D TMA bulk copies) plus the
+ * fp32 per-entity epilogue inputs (||w||, Nyquist coefficient, 1/hn, bt).  entity / hn / bt are in `dtype`
+ * (fp32 or fp64 models; bt may be NULL); rebuild it whenever one of them changes. */
+int chk_entity_shadow_build(int dtype, int rank, int64_t n_rows, const void* entity, const void* hn, const void* bt,
+                            void* shadow, void* stream);
 int64_t chk_rank_mma_workspace_bytes(int rank, int64_t b);
 /* Zero the workspace header (list length + sticky overflow flag); call once before a ranking pass. */
 int chk_rank_mma_reset(void* workspace, void* stream);
@@ -166,7 +171,7 @@ int chk_rank_mma_reset(void* workspace, void* stream);
 int chk_rank_mma_status(const void* workspace, int64_t* last_list_len, int* overflowed, void* stream);
 /* Test support (like chk_score_all): the tensor-core tier's approximate scores [b,n_rows] and error bands
  * [b,n_rows] (band 0 = decided exactly in the clamp regime), plus its counts (no filter pass). */
-int chk_score_all_mma(int rank, int64_t b, const void* q, const void* qn, const void* bh_vals,
+int chk_score_all_mma(int dtype, int rank, int64_t b, const void* q, const void* qn, const void* bh_vals,
                       const void* target, const void* entity, const void* hn, const void* bt, int64_t n_rows,
                       const void* shadow, void* workspace, int64_t workspace_bytes, int64_t* counts,
                       void* scores, void* band, void* stream);

@@ -22,7 +22,7 @@ def run(rank, n_ent, b, seed=0, regime="trained"):
     rows = ent[tails].contiguous()
     tgt = ops.target_scores(rank, q, qn, bh, rows, ops.row_hnorm(rank, rows), bt[tails].contiguous())
     S = ops.score_all(rank, q, qn, bh, ent, hn, bt)
-    shadow = ops.entity_shadow(rank, ent)
+    shadow = ops.entity_shadow(rank, ent, hn, bt)
     ws = ops.rank_mma_workspace(rank, b, ent.device)
     out = {}
     for swap in ("0",):
