@@ -31,6 +31,8 @@ SIGNATURES = {
     "chk_abi_version": (_i, []),
     "chk_last_error": (ctypes.c_char_p, []),
     "chk_query_fwd": (_i, [_i, _i, _i, _i64, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "chk_group_by_key": (_i, [_p, _i64, _i, _p, _p, _p]),
+    "chk_query_fwd_grouped": (_i, [_i, _i, _i, _i64, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "chk_query_bwd": (_i, [_i, _i, _i, _i64, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "chk_score_gather_fwd": (_i, [_i, _i, _i64, _i64, _p, _i64, _i64, _p, _p, _i64, _p, _i64, _i64, _p, _p, _p]),
     "chk_score_gather_bwd": (_i, [_i, _i, _i64, _i64, _p, _i64, _i64, _p, _p, _i64, _p, _p, _p, _p]),

@@ -655,6 +655,10 @@ QArgs<T> make_args(int64_t nq, int multi_c, const void* entity, const void* rel,
 
 }  // namespace
 
+int chk_query_fwd_tpq(int kind, int rank, int64_t nq, int multi_c, const void* entity, const void* rel, const void* rel_diag,
+                      const void* ctx, const void* c_table, const int64_t* head_idx, const int64_t* rel_idx,
+                      const int32_t* perm, void* out_q, void* out_c, cudaStream_t st);
+
 extern "C" int chk_query_fwd(int kind, int dtype, int rank, int64_t nq, int multi_c,
                              const void* entity, const void* rel, const void* rel_diag, const void* ctx,
                              const void* c_table, const int64_t* head_idx, const int64_t* rel_idx,
@@ -675,6 +679,29 @@ extern "C" int chk_query_fwd(int kind, int dtype, int rank, int64_t nq, int mult
     }
     chk_set_error("unknown dtype %d", dtype);
     return CHK_EINVAL;
+}
+
+int chk_group_by_key_impl(const int64_t* keys, int64_t n, int n_keys, int32_t* perm, int32_t* counts, cudaStream_t st);
+
+extern "C" int chk_group_by_key(const int64_t* keys, int64_t n, int n_keys, int32_t* perm, int32_t* counts_scratch, void* stream) {
+    if (n == 0) return CHK_OK;
+    if (n < 0 || !keys || !perm || !counts_scratch) { chk_set_error("chk_group_by_key: bad argument"); return CHK_EINVAL; }
+    return chk_group_by_key_impl(keys, n, n_keys, perm, counts_scratch, (cudaStream_t)stream);
+}
+
+extern "C" int chk_query_fwd_grouped(int kind, int dtype, int rank, int64_t nq, int multi_c,
+                                     const void* entity, const void* rel, const void* rel_diag, const void* ctx,
+                                     const void* c_table, const int64_t* head_idx, const int64_t* rel_idx, const int32_t* perm,
+                                     void* out_q, void* out_c, void* stream) {
+    if (nq == 0) return CHK_OK;
+    if (nq < 0 || !entity || !rel || !rel_diag || !c_table || !head_idx || !rel_idx || !out_q || !out_c) {
+        chk_set_error("chk_query_fwd_grouped: null pointer or negative size"); return CHK_EINVAL;
+    }
+    if (dtype != CHK_F32 || !(rank == 9 || rank == 17 || rank == 33)) {
+        chk_set_error("chk_query_fwd_grouped: fp32 and rank in {9,17,33} only (use chk_query_fwd)"); return CHK_EUNSUPPORTED;
+    }
+    return chk_query_fwd_tpq(kind, rank, nq, multi_c, entity, rel, rel_diag, ctx, c_table, head_idx, rel_idx, perm, out_q, out_c,
+                             (cudaStream_t)stream);
 }
 
 extern "C" int chk_query_bwd(int kind, int dtype, int rank, int64_t nq, int multi_c,

@@ -53,11 +53,35 @@ def supported_rank(rank: int) -> bool:
 
 
 # ------------------------------------------------------------------------------------------- raw calls
-def query_fwd(kind, rank, multi_c, entity, rel, rel_diag, ctx, c_table, head_idx, rel_idx):
+GROUPED_MIN_QUERIES = 1 << 16      # from here on the thread-per-query K1 (+ argsort by relation) beats the lane-group kernel
+
+
+def query_fwd(kind, rank, multi_c, entity, rel, rel_diag, ctx, c_table, head_idx, rel_idx, grouped=None):
+    """get_queries.  grouped=None picks the throughput variant (chk_query_fwd_grouped, queries processed in relation
+    order) for large fp32 batches at rank <= 33; True / False force it."""
     _chk(entity, rel, rel_diag, ctx, c_table, head_idx, rel_idx)
     nq = head_idx.numel()
     q = torch.empty((nq, 2 * rank), dtype=entity.dtype, device=entity.device)
     c = torch.empty((nq,), dtype=entity.dtype, device=entity.device)
+    can_group = entity.dtype == torch.float32 and rank in (9, 17, 33)
+    if grouped is None:
+        grouped = can_group and nq >= GROUPED_MIN_QUERIES
+    if grouped:
+        if not can_group:
+            raise RuntimeError("the grouped query transform is fp32, rank in {9, 17, 33} only")
+        n_keys = rel.shape[0]
+        if n_keys <= 12288:
+            perm = torch.empty((nq,), dtype=torch.int32, device=entity.device)
+            scratch = torch.empty((n_keys,), dtype=torch.int32, device=entity.device)
+            _lib.check(_lib.lib().chk_group_by_key(_p(rel_idx), nq, n_keys, _p(perm), _p(scratch), _stream()), "chk_group_by_key")
+            _launched(3)
+        else:
+            perm = torch.argsort(rel_idx).to(torch.int32)
+        _lib.check(_lib.lib().chk_query_fwd_grouped(kind, _dt(entity), rank, nq, int(multi_c), _p(entity), _p(rel),
+                                                    _p(rel_diag), _p(ctx), _p(c_table), _p(head_idx), _p(rel_idx), _p(perm),
+                                                    _p(q), _p(c), _stream()), "chk_query_fwd_grouped")
+        _launched(1)
+        return q, c
     _lib.check(_lib.lib().chk_query_fwd(kind, _dt(entity), rank, nq, int(multi_c), _p(entity), _p(rel), _p(rel_diag),
                                         _p(ctx), _p(c_table), _p(head_idx), _p(rel_idx), _p(q), _p(c), _stream()),
                "chk_query_fwd")

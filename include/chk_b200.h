@@ -41,6 +41,19 @@ int chk_query_fwd(int kind, int dtype, int rank, int64_t nq, int multi_c,
                   const void* c_table, const int64_t* head_idx, const int64_t* rel_idx,
                   void* out_q, void* out_c, void* stream);
 
+/* Same result as chk_query_fwd, THROUGHPUT variant for large batches (fp32, rank in {9,17,33}): one THREAD per query
+ * (register FFT with compile-time twiddles, thread-local norms, entity rows staged through shared memory with
+ * asynchronous copies), 2x the lane-group kernel at 2^20 queries when the 32 queries of a warp share their relation.
+ * perm (int32 [nq], may be NULL) is the order in which queries are processed — pass argsort(rel_idx) to group them by
+ * relation; outputs are written at the original query positions.  Latency at small nq is worse than chk_query_fwd. */
+/* perm = the positions 0..n-1 grouped by keys[i] in [0, n_keys) (counting sort; order inside a group unspecified).
+ * counts_scratch: int32 [n_keys].  n < 2^31, n_keys <= 12288. */
+int chk_group_by_key(const int64_t* keys, int64_t n, int n_keys, int32_t* perm, int32_t* counts_scratch, void* stream);
+int chk_query_fwd_grouped(int kind, int dtype, int rank, int64_t nq, int multi_c,
+                          const void* entity, const void* rel, const void* rel_diag, const void* ctx,
+                          const void* c_table, const int64_t* head_idx, const int64_t* rel_idx, const int32_t* perm,
+                          void* out_q, void* out_c, void* stream);
+
 /* Adjoint of chk_query_fwd (what autograd does through the ~35 eager ops of get_queries).
  * grad_q [nq,2r] in; per-query gradient ROWS out (the caller scatters them with chk_scatter_add_rows):
  * g_entity_rows [nq,2r], g_rel_rows [nq,2n], g_rel_diag_rows [nq,n] ([nq,2n] for ATT),

@@ -327,3 +327,27 @@ def test_edge_cases():
     ex = torch.tensor([[1, 0, 2], [3, 1, 4]])
     ranks = m2.get_ranking(ex, {(1, 0): [2, 7], (3, 1): [4]}, batch_size=2)
     assert ranks.tolist() == [500 - 2 + 1, 500 - 1 + 1]
+
+
+@pytest.mark.parametrize("name", ["FFTRotH", "FFTRefH", "FFTAttH"])
+@pytest.mark.parametrize("rank", [9, 17, 33])
+def test_grouped_query_transform_matches_lane_group_kernel(name, rank):
+    """chk_query_fwd_grouped (thread-per-query K1, queries processed in relation order) vs chk_query_fwd on the same
+    inputs, ragged batch, multi_c on/off, and vs the oracle."""
+    from complexhyperbolickge_b200 import ops
+    from oracle import chk_oracle as O
+    for multi_c in (True, False):
+        p = _random_params(name, rank, 900, 14, torch.float32, multi_c, seed=rank + 3)
+        model = _model_from_params(p, name)
+        g = torch.Generator().manual_seed(rank)
+        nq = 1000 + 7
+        h, r = torch.randint(0, 900, (nq,), generator=g), torch.randint(0, 14, (nq,), generator=g)
+        args = (model.KIND, rank, multi_c, model.entity.weight.detach(), model.rel.weight.detach(),
+                model.rel_diag.weight.detach(), None if model._ctx_weight() is None else model._ctx_weight().detach(),
+                model.c.weight.detach(), h.cuda(), r.cuda())
+        q0, c0 = ops.query_fwd(*args, grouped=False)
+        q1, c1 = ops.query_fwd(*args, grouped=True)
+        assert torch.equal(c0, c1)
+        _close(q1, q0.cpu().numpy(), 2e-6, "grouped vs lane-group get_queries")
+        q_ref, _ = O.query_fwd(p, h, r)
+        _close(q1, q_ref.numpy(), 3e-5, "grouped get_queries vs oracle")

@@ -47,13 +47,17 @@ def k1(kind, name, rank, nq, n_ent, n_rel2, dtype):
     c = torch.rand(n_rel2, 1, generator=g, device="cuda", dtype=dtype) + 0.5
     h = torch.randint(0, n_ent, (nq,), generator=g, device="cuda")
     r = torch.randint(0, n_rel2, (nq,), generator=g, device="cuda")
-    ms = timeit(lambda: ops.query_fwd(kind, rank, True, ent, rel, rd, ctx, c, h, r))
+    ms = timeit(lambda: ops.query_fwd(kind, rank, True, ent, rel, rd, ctx, c, h, r, grouped=False))
     byt = nq * (2 * 2 * rank * es + 16)                       # entity row in, query row out, ids
+    ms_s = float("nan")
+    if dtype == torch.float32 and rank <= 33 and nq >= 4096:  # thread-per-query variant incl. its argsort by relation
+        ms_s = timeit(lambda: ops.query_fwd(kind, rank, True, ent, rel, rd, ctx, c, h, r, grouped=True))
     gq = torch.randn(nq, 2 * rank, generator=g, device="cuda", dtype=dtype)
     msb = timeit(lambda: ops.query_bwd(kind, rank, True, ent, rel, rd, ctx, c, h, r, gq))
     wrel = 2 * n + (2 * n if kind == ops.CHK_ATT else n) + (n if kind == ops.CHK_ATT else 0) + 1
     bytb = nq * ((2 * 2 * rank + 2 * rank + wrel) * es + 16)  # entity row + grad_q in, grad rows out
     print(f"K1 {name:8s} r={rank:3d} {str(dtype)[6:]:7s} nq={nq}: fwd {ms:7.3f} ms {byt / ms / 1e6:7.0f} GB/s ({byt / ms / 1e6 / PEAK:5.1%})"
+          f" [thread-per-query + argsort by relation {ms_s:7.3f} ms {byt / ms_s / 1e6 / PEAK:5.1%}]"
           f"   bwd {msb:7.3f} ms {bytb / msb / 1e6:7.0f} GB/s ({bytb / msb / 1e6 / PEAK:5.1%})", flush=True)
 
 
