@@ -53,6 +53,7 @@ SIGNATURES = {
     "chk_rank_mma_workspace_bytes": (_i64, [_i, _i64]),
     "chk_rank_mma_reset": (_i, [_p, _p]),
     "chk_rank_mma_status": (_i, [_p, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int), _p]),
+    "chk_rank_mma_profile_events": (_i, [_p, _p]),
     "chk_score_all_mma": (_i, [_i, _i, _i64, _p, _p, _p, _p, _p, _p, _p, _i64, _p, _p, _i64, _p, _p, _p, _p]),
 }
 

@@ -164,6 +164,16 @@ template <typename T> struct RArgs {
 // shared-memory transpose.  Used wherever a list of scattered (query, entity) pairs must be scored exactly:
 // the filter pass and the re-check of the tensor-core tier.
 template <typename T> struct PairTiles { T zr[32][33], zi[32][33], wr[32][33], wi[32][33]; };
+// fp32: WHOLE rows of 8 pairs are staged per pass (consecutive copies walk one row, so DRAM sees 2 KB runs instead of
+// scattered 128-byte pieces); every canonical 16-coefficient block sits in a 20-float slot and rows are 688 floats
+// apart (= 16 mod 32), which makes the 128-bit reads of a quarter-warp (2 pairs x 4 lanes) hit 32 distinct banks.
+template <> struct __align__(16) PairTiles<float> {
+    static constexpr int BS = 20;                    // floats per staged block
+    static constexpr int PL = 17 * BS;               // one plane (Re or Im): 16 full blocks + the tail block (rank <= 257)
+    static constexpr int RS = 688;                   // row stride (2 * PL = 680, padded)
+    static constexpr int SLOTS = 8;                  // pairs per pass
+    float z[SLOTS][RS], w[SLOTS][RS];
+};
 
 __device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
@@ -172,7 +182,10 @@ __device__ __forceinline__ void cp_async_8(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// fp64 (and the generic fallback): 32-coefficient chunks, single-buffered.
 template <typename T>
 __device__ __forceinline__ T warp_exact_pairs(const RArgs<T>& A, unsigned i, unsigned e, bool valid, PairTiles<T>& S) {
     const int lane = threadIdx.x & 31;
@@ -189,31 +202,112 @@ __device__ __forceinline__ T warp_exact_pairs(const RArgs<T>& A, unsigned i, uns
             if (vp && lane < kc) {
                 const T* z = A.q + (size_t)ip * 2 * r + k0 + lane;
                 const T* w = A.entity + (size_t)ep * 2 * r + k0 + lane;
-                if (sizeof(T) == 4) {
-                    cp_async_4(&S.zr[p][lane], z); cp_async_4(&S.zi[p][lane], z + r);
-                    cp_async_4(&S.wr[p][lane], w); cp_async_4(&S.wi[p][lane], w + r);
-                } else {
-                    cp_async_8(&S.zr[p][lane], z); cp_async_8(&S.zi[p][lane], z + r);
-                    cp_async_8(&S.wr[p][lane], w); cp_async_8(&S.wi[p][lane], w + r);
-                }
+                cp_async_8(&S.zr[p][lane], z); cp_async_8(&S.zi[p][lane], z + r);
+                cp_async_8(&S.wr[p][lane], w); cp_async_8(&S.wi[p][lane], w + r);
             }
         }
         cp_async_wait_all();
         __syncwarp();
-        if (valid) {
-            if (Chain<T>::BLK == 0) {
-                for (int kk = 0; kk < kc; ++kk) dot_step<T>(S.zr[lane][kk], S.zi[lane][kk], S.wr[lane][kk], S.wi[lane][kk], re, im);
-            } else {                                 // k0 is a multiple of 32: block boundaries fall at kk = 0, 16
-                for (int b0 = 0; b0 < kc; b0 += Chain<T>::BLK) {
-                    T pr = T(0), pi = T(0);
-                    const int b1 = min(b0 + Chain<T>::BLK, kc);
-                    for (int kk = b0; kk < b1; ++kk) dot_step<T>(S.zr[lane][kk], S.zi[lane][kk], S.wr[lane][kk], S.wi[lane][kk], pr, pi);
-                    re = Sc<T>::add_(re, pr); im = Sc<T>::add_(im, pi);
-                }
-            }
-        }
+        if (valid)
+            for (int kk = 0; kk < kc; ++kk) dot_step<T>(S.zr[lane][kk], S.zi[lane][kk], S.wr[lane][kk], S.wi[lane][kk], re, im);
     }
     if (!valid) return T(0);
     const bool has_bias = A.bt != nullptr;
     return pair_score<T>(re, im, A.qn[i], A.hn[e], has_bias, has_bias ? A.bh_vals[i] : T(0), has_bias ? A.bt[e] : T(0));
+}
+
+// fp32: the canonical order is BLOCKED (Chain<float>::BLK = 16): the blocks of a pair are independent chains whose
+// partial sums are added in ascending block order.  A pass handles 8 pairs; FOUR lanes share a pair, lane `sub` walks
+// blocks sub, sub+4, ... and after every round of four blocks the partials are folded into the running sum in block
+// order (shuffles), so the bits equal exact_pair()'s.  Results return to the lane that owns the pair.
+// R > 0: the rank is a compile-time constant (every loop unrolls, the copies use immediate offsets); R = 0: runtime rank.
+template <int R>
+__device__ __forceinline__ void exact_pairs_f32(const RArgs<float>& A, unsigned i, unsigned e, bool valid, PairTiles<float>& S,
+                                                float& my_re, float& my_im) {
+    using PT = PairTiles<float>;
+    constexpr int BLK = Chain<float>::BLK, BS = PT::BS, PL = PT::PL;
+    static_assert(BLK == 16, "staging assumes 16-coefficient blocks");
+    const int lane = threadIdx.x & 31;
+    const int r = R ? R : A.r;
+    const int nfull = r / BLK, tail = r - nfull * BLK;
+    const int c_lane = (lane >> 4) * BS + (lane & 15);                  // staged position of coefficient k0 + lane (k0 % 32 == 0)
+    for (int pass = 0; pass < 4; ++pass) {
+        if (!__any_sync(CHK_FULL, valid && (lane >> 3) == pass)) continue;
+        __syncwarp();                                                   // readers of the previous pass / call are done with S
+#pragma unroll
+        for (int sl = 0; sl < PT::SLOTS; ++sl) {
+            const int src = pass * 8 + sl;
+            const unsigned ip = __shfl_sync(CHK_FULL, i, src), ep = __shfl_sync(CHK_FULL, e, src);
+            if (!__shfl_sync(CHK_FULL, (int)valid, src)) continue;
+            const float* zrow = A.q + (size_t)ip * 2 * r + lane;
+            const float* wrow = A.entity + (size_t)ep * 2 * r + lane;
+            float* zd = &S.z[sl][c_lane];
+            float* wd = &S.w[sl][c_lane];
+#pragma unroll
+            for (int k0 = 0; k0 < r; k0 += 32) {                        // Re plane, then Im plane: one contiguous run per row
+                const int d = (k0 >> 5) * 2 * BS;
+                if (k0 + 32 <= r || k0 + lane < r) { cp_async_4(wd + d, wrow + k0); cp_async_4(zd + d, zrow + k0); }
+            }
+#pragma unroll
+            for (int k0 = 0; k0 < r; k0 += 32) {
+                const int d = PL + (k0 >> 5) * 2 * BS;
+                if (k0 + 32 <= r || k0 + lane < r) { cp_async_4(wd + d, wrow + r + k0); cp_async_4(zd + d, zrow + r + k0); }
+            }
+        }
+        cp_async_wait_all();
+        __syncwarp();
+        const int sl = lane >> 2, sub = lane & 3, base = lane & ~3;
+        const float* zb = S.z[sl];
+        const float* wb = S.w[sl];
+        float re = 0.f, im = 0.f;
+#pragma unroll
+        for (int b0 = 0; b0 < nfull; b0 += 4) {
+            const int b = b0 + sub;
+            float pr = 0.f, pi = 0.f;
+            if (b < nfull) {
+                const float* zq = zb + b * BS;
+                const float* wq = wb + b * BS;
+#pragma unroll
+                for (int k4 = 0; k4 < BLK; k4 += 4) {
+                    const float4 zr = *reinterpret_cast<const float4*>(zq + k4);
+                    const float4 zi = *reinterpret_cast<const float4*>(zq + PL + k4);
+                    const float4 wr = *reinterpret_cast<const float4*>(wq + k4);
+                    const float4 wi = *reinterpret_cast<const float4*>(wq + PL + k4);
+                    dot_step<float>(zr.x, zi.x, wr.x, wi.x, pr, pi);
+                    dot_step<float>(zr.y, zi.y, wr.y, wi.y, pr, pi);
+                    dot_step<float>(zr.z, zi.z, wr.z, wi.z, pr, pi);
+                    dot_step<float>(zr.w, zi.w, wr.w, wi.w, pr, pi);
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {                               // fold the four partials in ascending block order
+                const float tr = __shfl_sync(CHK_FULL, pr, base + t), ti = __shfl_sync(CHK_FULL, pi, base + t);
+                if (b0 + t < nfull) { re = Sc<float>::add_(re, tr); im = Sc<float>::add_(im, ti); }
+            }
+        }
+        if (tail > 0) {                                                 // the last (short) block, by all four lanes alike
+            float pr = 0.f, pi = 0.f;
+            const float* zq = zb + nfull * BS;
+            const float* wq = wb + nfull * BS;
+            for (int kk = 0; kk < tail; ++kk) dot_step<float>(zq[kk], zq[PL + kk], wq[kk], wq[PL + kk], pr, pi);
+            re = Sc<float>::add_(re, pr); im = Sc<float>::add_(im, pi);
+        }
+        const float vr = __shfl_sync(CHK_FULL, re, (lane & 7) * 4), vi = __shfl_sync(CHK_FULL, im, (lane & 7) * 4);
+        if ((lane >> 3) == pass) { my_re = vr; my_im = vi; }
+    }
+}
+
+template <>
+__device__ __forceinline__ float warp_exact_pairs<float>(const RArgs<float>& A, unsigned i, unsigned e, bool valid, PairTiles<float>& S) {
+    float my_re = 0.f, my_im = 0.f;
+    switch (A.r) {                                   // the supported ranks are 2^m + 1
+        case 33: exact_pairs_f32<33>(A, i, e, valid, S, my_re, my_im); break;
+        case 65: exact_pairs_f32<65>(A, i, e, valid, S, my_re, my_im); break;
+        case 129: exact_pairs_f32<129>(A, i, e, valid, S, my_re, my_im); break;
+        case 257: exact_pairs_f32<257>(A, i, e, valid, S, my_re, my_im); break;
+        default: exact_pairs_f32<0>(A, i, e, valid, S, my_re, my_im); break;
+    }
+    if (!valid) return 0.f;
+    const bool has_bias = A.bt != nullptr;
+    return pair_score<float>(my_re, my_im, A.qn[i], A.hn[e], has_bias, has_bias ? A.bh_vals[i] : 0.f, has_bias ? A.bt[e] : 0.f);
 }

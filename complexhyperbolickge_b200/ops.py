@@ -286,6 +286,13 @@ def rank_mma_status(workspace):
     return n.value, bool(ov.value)
 
 
+def rank_mma_profile_events(start=None, stop=None):
+    """Measurement support: arm (two recorded torch.cuda.Event(enable_timing=True)) or disarm (None, None) the events the
+    library records immediately around rank_mma_kernel inside chk_rank_counts."""
+    h = lambda ev: None if ev is None else ev.cuda_event
+    _lib.check(_lib.lib().chk_rank_mma_profile_events(h(start), h(stop)), "chk_rank_mma_profile_events")
+
+
 def score_all_mma(rank, q, qn, bh_vals, target, entity, hn, bt, shadow, workspace):
     """Test support: tensor-core tier approximate scores, error bands and (unfiltered) counts."""
     _chk(q, qn, bh_vals, target, entity, hn, bt, shadow, workspace)

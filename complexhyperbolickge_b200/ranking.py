@@ -82,13 +82,73 @@ def rank_batch(model, state: EvalState, queries_dev: torch.Tensor, indptr_dev, i
     return target
 
 
+class _HostRing:
+    """Pinned host staging for the evaluation pipeline: DEPTH int64 slots for the per-batch inputs (query ids +
+    filter CSR travel as ONE host->device copy) and one float32 result buffer.  A slot is reused only after the
+    copy that read it has completed (per-slot event), so the host can run several batches ahead of the GPU."""
+    DEPTH = 3
+
+    def __init__(self):
+        self.slots = [None] * self.DEPTH
+        self.events = [None] * self.DEPTH
+        self.result = None
+        self.turn = 0
+
+    def stage(self, n_words: int):
+        s = self.turn
+        self.turn = (s + 1) % self.DEPTH
+        if self.events[s] is not None:
+            self.events[s].synchronize()
+        buf = self.slots[s]
+        if buf is None or buf.numel() < n_words:
+            buf = self.slots[s] = torch.empty(max(2 * n_words, 1 << 14), dtype=torch.int64, pin_memory=True)
+        return s, buf
+
+    def sent(self, s: int):
+        if self.events[s] is None:
+            self.events[s] = torch.cuda.Event()
+        self.events[s].record()
+
+    def result_buffer(self, n: int):
+        if self.result is None or self.result.numel() < n:
+            self.result = torch.empty(max(n, 1 << 12), dtype=torch.float32, pin_memory=True)
+        return self.result
+
+
+def _send_batch(ring: _HostRing, qb: np.ndarray, indptr: np.ndarray, idx: np.ndarray, dev):
+    """Pack (queries [b,3], indptr [b+1], idx [tot]) into one pinned slot, ONE async H2D copy; returns device views."""
+    b, tot = qb.shape[0], int(idx.size)
+    n_words = 3 * b + (b + 1) + max(tot, 1)
+    s, host = ring.stage(n_words)
+    hv = host.numpy()
+    hv[:3 * b] = qb.reshape(-1)
+    hv[3 * b:4 * b + 1] = indptr
+    if tot:
+        hv[4 * b + 1:4 * b + 1 + tot] = idx
+    else:
+        hv[4 * b + 1] = 0
+    d = host[:n_words].to(dev, non_blocking=True)
+    ring.sent(s)
+    return d[:3 * b].view(b, 3), d[3 * b:4 * b + 1], d[4 * b + 1:], tot, 8 * n_words
+
+
 def rank_queries(model, queries: torch.Tensor, findex: FilterIndex, batch_size: int) -> torch.Tensor:
+    """Filtered ranks of all queries, float32 CPU tensor [n].  The batches form a pipeline: while the GPU counts
+    batch i the host builds the filter CSR of batch i+1 in pinned memory; every batch has one H2D copy of its
+    inputs and one asynchronous D2H copy of its ranks; the host synchronises ONCE, at the end of the pass."""
     dev = model.entity.weight.device
     if dev.type != "cuda":
         raise RuntimeError("complexhyperbolickge_b200 models run on CUDA only (no CPU fallback)")
     n = queries.shape[0]
     q_np = queries.cpu().numpy() if isinstance(queries, torch.Tensor) else np.asarray(queries)
-    counts_all = torch.zeros(n, dtype=torch.int64, device=dev)
+    q_np = np.ascontiguousarray(q_np, dtype=np.int64)
+    if n == 0:
+        return torch.empty(0, dtype=torch.float32)
+    ring = getattr(model, "_eval_ring", None)
+    if ring is None:
+        ring = model._eval_ring = _HostRing()
+    out_host = ring.result_buffer(n)
+    model.last_eval_io = io = {"h2d_bytes": 0, "d2h_bytes": 0, "batches": 0}
     with torch.no_grad():
         state = eval_state(model)
         ws = None
@@ -99,30 +159,30 @@ def rank_queries(model, queries: torch.Tensor, findex: FilterIndex, batch_size: 
             ws = ws[1]
             ops.rank_mma_reset(ws)
         nan_seen = torch.zeros((), dtype=torch.bool, device=dev)
-        for b0 in range(0, n, batch_size):
-            qb = q_np[b0:b0 + batch_size]
-            indptr, idx = findex.batch_csr(qb)
-            qd = torch.from_numpy(np.ascontiguousarray(qb)).to(dev, non_blocking=True)
-            ip = torch.from_numpy(indptr).to(dev, non_blocking=True)
-            ix = torch.from_numpy(idx).to(dev, non_blocking=True) if idx.size else torch.zeros(1, dtype=torch.int64, device=dev)
-            target = rank_batch(model, state, qd, ip, ix, int(idx.size), counts_all[b0:b0 + batch_size], ws)
-            nan_seen |= torch.isnan(target).any()         # models/base.py:259-260, checked once after the pass (no per-batch sync)
-        if ws is not None and ops.rank_mma_status(ws)[1]:
-            # the re-check list of some batch overflowed (pathological tie mass): redo the pass on the exact tier
-            state = EvalState.__new__(EvalState)
-            state.__dict__.update(eval_state(model).__dict__)
-            state.algo, state.shadow = ops.CHK_RANK_FMA, None
-            counts_all.zero_()
+
+        def one_pass(state, ws):
             for b0 in range(0, n, batch_size):
                 qb = q_np[b0:b0 + batch_size]
                 indptr, idx = findex.batch_csr(qb)
-                qd = torch.from_numpy(np.ascontiguousarray(qb)).to(dev)
-                ix = torch.from_numpy(idx).to(dev) if idx.size else torch.zeros(1, dtype=torch.int64, device=dev)
-                rank_batch(model, state, qd, torch.from_numpy(indptr).to(dev), ix, int(idx.size),
-                           counts_all[b0:b0 + batch_size], None)
-        if state.world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(counts_all, op=dist.ReduceOp.SUM, group=model.process_group)
-    ranks = (counts_all + 1).to(torch.float32).cpu()
-    assert not bool(nan_seen), "NaN score in get_ranking"
-    return ranks
+                qd, ip, ix, tot, nbytes = _send_batch(ring, qb, indptr, idx, dev)
+                counts = torch.zeros(qb.shape[0], dtype=torch.int64, device=dev)
+                target = rank_batch(model, state, qd, ip, ix, tot, counts, ws)
+                if state.world > 1:                      # integer partial counts of the entity shards
+                    import torch.distributed as dist
+                    dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=model.process_group)
+                out_host[b0:b0 + qb.shape[0]].copy_((counts + 1).to(torch.float32), non_blocking=True)
+                nan_seen.logical_or_(torch.isnan(target).any())   # models/base.py:259-260, checked once after the pass
+                io["h2d_bytes"] += nbytes
+                io["d2h_bytes"] += 4 * qb.shape[0]
+                io["batches"] += 1
+
+        one_pass(state, ws)
+        if ws is not None and ops.rank_mma_status(ws)[1]:
+            # the re-check list of some batch overflowed (pathological tie mass): redo the pass on the exact tier
+            exact = EvalState.__new__(EvalState)
+            exact.__dict__.update(state.__dict__)
+            exact.algo, exact.shadow = ops.CHK_RANK_FMA, None
+            one_pass(exact, None)
+        nan_host = bool(nan_seen)                        # synchronises the stream: every D2H copy above has landed
+    assert not nan_host, "NaN score in get_ranking"
+    return out_host[:n].clone()

@@ -182,6 +182,10 @@ int64_t chk_rank_mma_workspace_bytes(int rank, int64_t b);
 int chk_rank_mma_reset(void* workspace, void* stream);
 /* Synchronises `stream` and reads the header back: length of the last re-check list, sticky overflow flag. */
 int chk_rank_mma_status(const void* workspace, int64_t* last_list_len, int* overflowed, void* stream);
+/* Measurement support: while armed (non-NULL cudaEvent_t handles, per calling thread), every CHK_RANK_MMA launch of
+ * this thread records ev_start / ev_stop on its stream immediately around rank_mma_kernel (the dominant kernel), so
+ * a benchmark can time that kernel alone inside a whole chk_rank_counts call.  Pass NULL, NULL to disarm. */
+int chk_rank_mma_profile_events(void* ev_start, void* ev_stop);
 /* Test support (like chk_score_all): the tensor-core tier's approximate scores [b,n_rows] and error bands
  * [b,n_rows] (band 0 = decided exactly in the clamp regime), plus its counts (no filter pass). */
 int chk_score_all_mma(int dtype, int rank, int64_t b, const void* q, const void* qn, const void* bh_vals,
