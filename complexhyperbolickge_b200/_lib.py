@@ -40,6 +40,7 @@ SIGNATURES = {
     "chk_nsloss": (_i, [_i, _i64, _i64, _p, _p, _p, _p]),
     "chk_sparse_adagrad": (_i, [_i, _p, _p, _p, _p, _i64, _i64, ctypes.c_double, ctypes.c_double, _p, _p, _p]),
     "chk_step_counter_bump": (_i, [_p, _p]),
+    "chk_claim_gather_rows": (_i, [_i, _p, _p, _i64, _i64, _p, _p, _p, _p]),
     "chk_multi_scatter_add": (_i, [_i, ctypes.POINTER(TableDesc), _i, _p]),
     "chk_multi_sparse_adagrad": (_i, [_i, ctypes.POINTER(TableDesc), _i, ctypes.c_double, ctypes.c_double, _p, _p]),
     "chk_scatter_add_rows": (_i, [_i, _p, _p, _p, _i64, _i64, _p]),

@@ -42,6 +42,44 @@ __global__ void __launch_bounds__(256) nsloss_kernel(const T* __restrict__ s, in
     }
 }
 
+// Adagrad on one row by one warp.  Even widths (every 2r-wide / n-wide table: rows are 8-byte aligned) go two elements
+// per lane with all loads of an iteration pair issued before the arithmetic; odd widths (bh, bt, c) take the scalar loop.
+template <typename T>
+__device__ __forceinline__ void adagrad_elem(T& pv, T& gv, T& av, T lr, T eps) {
+    av = Sc<T>::fma_(gv, gv, av);
+    pv -= lr * gv / (Sc<T>::sqrt_(av) + eps);
+    gv = T(0);
+}
+template <typename T> struct Vec2;
+template <> struct Vec2<float> { using type = float2; };
+template <> struct Vec2<double> { using type = double2; };
+template <typename T>
+__device__ __forceinline__ void adagrad_row(T* __restrict__ p, T* __restrict__ g, T* __restrict__ a, int64_t width, int lane, T lr, T eps) {
+    using V = typename Vec2<T>::type;
+    if ((width & 1) == 0) {
+        V* p2 = reinterpret_cast<V*>(p); V* g2 = reinterpret_cast<V*>(g); V* a2 = reinterpret_cast<V*>(a);
+        const int64_t w2 = width >> 1;
+        int64_t c = lane;
+        for (; c + 32 < w2; c += 64) {
+            V g0 = g2[c], g1 = g2[c + 32], a0 = a2[c], a1 = a2[c + 32], p0 = p2[c], p1 = p2[c + 32];
+            adagrad_elem<T>(p0.x, g0.x, a0.x, lr, eps); adagrad_elem<T>(p0.y, g0.y, a0.y, lr, eps);
+            adagrad_elem<T>(p1.x, g1.x, a1.x, lr, eps); adagrad_elem<T>(p1.y, g1.y, a1.y, lr, eps);
+            a2[c] = a0; a2[c + 32] = a1; p2[c] = p0; p2[c + 32] = p1; g2[c] = g0; g2[c + 32] = g1;
+        }
+        for (; c < w2; c += 32) {
+            V g0 = g2[c], a0 = a2[c], p0 = p2[c];
+            adagrad_elem<T>(p0.x, g0.x, a0.x, lr, eps); adagrad_elem<T>(p0.y, g0.y, a0.y, lr, eps);
+            a2[c] = a0; p2[c] = p0; g2[c] = g0;
+        }
+    } else {
+        for (int64_t c = lane; c < width; c += 32) {
+            T gv = g[c], av = a[c], pv = p[c];
+            adagrad_elem<T>(pv, gv, av, lr, eps);
+            a[c] = av; p[c] = pv; g[c] = gv;
+        }
+    }
+}
+
 // one warp per list entry; stamp[row] == *step_id marks "already updated in this step"
 template <typename T>
 __global__ void __launch_bounds__(256) sparse_adagrad_kernel(T* __restrict__ param, T* __restrict__ grad, T* __restrict__ sum,
@@ -56,17 +94,34 @@ __global__ void __launch_bounds__(256) sparse_adagrad_kernel(T* __restrict__ par
         first = __shfl_sync(CHK_FULL, first, 0);
         if (!first) continue;
         T* p = param + row * width; T* g = grad + row * width; T* a = sum + row * width;
-        for (int64_t c = lane; c < width; c += 32) {
-            const T gv = g[c];
-            const T s2 = Sc<T>::fma_(gv, gv, a[c]);
-            a[c] = s2;
-            p[c] -= lr * gv / (Sc<T>::sqrt_(s2) + eps);
-            g[c] = T(0);
-        }
+        adagrad_row<T>(p, g, a, width, lane, lr, eps);
     }
 }
 
 __global__ void bump_kernel(int* c) { *c += 1; }
+
+// Data-parallel sparse exchange, send side: slot t carries the WHOLE accumulated gradient row rows[t] if it is the
+// first slot of this step naming that row (claimed through stamp[row] = -step, a token the Adagrad kernel never
+// writes), zeros otherwise; the claimed row of the dense gradient is cleared (the sum over ranks is scattered back).
+template <typename T>
+__global__ void __launch_bounds__(256) claim_gather_kernel(T* __restrict__ grad, const int64_t* __restrict__ rows, int64_t m,
+                                                           int64_t width, int* __restrict__ stamp, const int* __restrict__ step_id,
+                                                           T* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int token = -(*step_id);
+    for (int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < m; t += (int64_t)gridDim.x * (blockDim.x >> 5)) {
+        const int64_t row = rows[t];
+        int first = 0;
+        if (lane == 0) first = atomicExch(stamp + row, token) != token;
+        first = __shfl_sync(CHK_FULL, first, 0);
+        T* g = grad + row * width; T* o = out + t * width;
+        for (int64_t c = lane; c < width; c += 32) {
+            T v = T(0);
+            if (first) { v = g[c]; g[c] = T(0); }
+            o[c] = v;
+        }
+    }
+}
 
 // ---- multi-table variants: one launch walks up to CHK_MAX_TABLES tables (blockIdx.y = table) ---------------------
 struct TabList { chk_table_desc t[CHK_MAX_TABLES]; };
@@ -76,10 +131,18 @@ __global__ void __launch_bounds__(256) multi_scatter_kernel(TabList L) {
     const chk_table_desc d = L.t[blockIdx.y];
     if (!d.src_rows) return;
     T* dense = (T*)d.grad; const T* src = (const T*)d.src_rows;
-    const int64_t total = d.m * d.width;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t rrow = i / d.width, c = i - rrow * d.width;
-        atomicAdd(dense + d.rows[rrow] * d.width + c, src[i]);
+    if (d.width < 32) {                                  // narrow tables (bh, bt, c): one thread per element
+        const int64_t total = d.m * d.width;
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+            const int64_t rrow = i / d.width, c = i - rrow * d.width;
+            atomicAdd(dense + d.rows[rrow] * d.width + c, src[i]);
+        }
+        return;
+    }
+    const int lane = threadIdx.x & 31;                   // wide tables: one warp per row, coalesced reductions
+    for (int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < d.m; t += (int64_t)gridDim.x * (blockDim.x >> 5)) {
+        T* g = dense + d.rows[t] * d.width; const T* v = src + t * d.width;
+        for (int64_t c = lane; c < d.width; c += 32) atomicAdd(g + c, v[c]);
     }
 }
 
@@ -96,13 +159,7 @@ __global__ void __launch_bounds__(256) multi_adagrad_kernel(TabList L, T lr, T e
         first = __shfl_sync(CHK_FULL, first, 0);
         if (!first) continue;
         T* p = param + row * d.width; T* g = grad + row * d.width; T* a = sum + row * d.width;
-        for (int64_t c = lane; c < d.width; c += 32) {
-            const T gv = g[c];
-            const T s2 = Sc<T>::fma_(gv, gv, a[c]);
-            a[c] = s2;
-            p[c] -= lr * gv / (Sc<T>::sqrt_(s2) + eps);
-            g[c] = T(0);
-        }
+        adagrad_row<T>(p, g, a, d.width, lane, lr, eps);
     }
 }
 
@@ -135,6 +192,20 @@ extern "C" int chk_sparse_adagrad(int dtype, void* param, void* grad, void* stat
     return CHK_OK;
 }
 
+extern "C" int chk_claim_gather_rows(int dtype, void* grad, const int64_t* rows, int64_t m, int64_t width, int32_t* stamp,
+                                     const int32_t* step_id, void* out_rows, void* stream) {
+    if (m == 0 || width == 0) return CHK_OK;
+    if (m < 0 || width < 0 || !grad || !rows || !stamp || !step_id || !out_rows) { chk_set_error("chk_claim_gather_rows: bad argument"); return CHK_EINVAL; }
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t blocks = (m + 7) / 8;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (dtype == CHK_F32) claim_gather_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((float*)grad, rows, m, width, stamp, step_id, (float*)out_rows);
+    else if (dtype == CHK_F64) claim_gather_kernel<double><<<(unsigned)blocks, 256, 0, st>>>((double*)grad, rows, m, width, stamp, step_id, (double*)out_rows);
+    else { chk_set_error("unknown dtype %d", dtype); return CHK_EINVAL; }
+    CHK_CUDA_LAUNCH_CHECK("claim_gather_kernel");
+    return CHK_OK;
+}
+
 extern "C" int chk_step_counter_bump(int32_t* counter, void* stream) {
     if (!counter) { chk_set_error("chk_step_counter_bump: null"); return CHK_EINVAL; }
     bump_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(counter);
@@ -163,7 +234,7 @@ extern "C" int chk_multi_scatter_add(int dtype, const chk_table_desc* tabs, int 
     int rc = check_tabs(tabs, n_tables, true, false, L, mx, 256);
     if (rc != CHK_OK) return rc;
     if (mx == 0) return CHK_OK;
-    int64_t bx = (mx + 255) / 256; if (bx > 148 * 4) bx = 148 * 4;
+    int64_t bx = (mx + 255) / 256; if (bx > 148 * 8) bx = 148 * 8;
     dim3 grid((unsigned)bx, (unsigned)n_tables);
     if (dtype == CHK_F32) multi_scatter_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(L);
     else if (dtype == CHK_F64) multi_scatter_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>(L);

@@ -184,6 +184,20 @@ def multi_sparse_adagrad(tables, lr, eps, step_id):
     _launched(1)
 
 
+def claim_gather_rows(grad, rows, stamp, step_id, out=None):
+    """Send side of the data-parallel sparse exchange: [m, width] gradient rows (duplicate slots carry zeros), the
+    claimed rows of the dense ``grad`` are cleared."""
+    _chk(grad, rows, stamp, step_id, out)
+    width = grad.shape[1] if grad.dim() > 1 else 1
+    m = rows.numel()
+    if out is None:
+        out = torch.empty((m, width), dtype=grad.dtype, device=grad.device)
+    _lib.check(_lib.lib().chk_claim_gather_rows(_dt(grad), _p(grad), _p(rows), m, width, _p(stamp), _p(step_id), _p(out),
+                                                _stream()), "chk_claim_gather_rows")
+    _launched(1)
+    return out
+
+
 def step_counter_bump(counter):
     _chk(counter)
     _lib.check(_lib.lib().chk_step_counter_bump(_p(counter), _stream()), "chk_step_counter_bump")

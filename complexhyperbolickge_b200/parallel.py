@@ -40,7 +40,7 @@ def exchange_sparse_rows(grad: torch.Tensor, rows: torch.Tensor, pg=None) -> tor
     if world == 1:
         return grad
     rows = torch.unique(rows)
-    vals = grad.index_select(0, rows)
+    vals = grad.index_select(0, rows) / world      # only the touched rows are scaled: no pass over the N x w table
     n_local = torch.tensor([rows.numel()], dtype=torch.int64, device=grad.device)
     counts = [torch.zeros_like(n_local) for _ in range(world)]
     dist.all_gather(counts, n_local, group=pg)
@@ -58,7 +58,6 @@ def exchange_sparse_rows(grad: torch.Tensor, rows: torch.Tensor, pg=None) -> tor
         nk = int(counts[k].item())
         if nk:
             grad.index_add_(0, all_rows[k][:nk], all_vals[k][:nk])
-    grad.div_(world)
     return grad
 
 
@@ -147,7 +146,9 @@ class FusedDataParallelKGOptimizer(FusedKGOptimizer):
 
     Local gradients are pre-scaled by 1/world, so the summed gradient is the gradient of the global mean loss."""
 
-    def __init__(self, *args, process_group=None, **kw):
+    def __init__(self, *args, process_group=None, sparse_exchange=None, **kw):
+        """sparse_exchange: None = decide per table by size (below); True = the row-sparse tables (entity, bh, bt)
+        always use the sparse row exchange (tests / small-scale checks of the big-table path)."""
         super().__init__(*args, **kw)
         self.pg = process_group
         self.world = _world(process_group)
@@ -161,8 +162,11 @@ class FusedDataParallelKGOptimizer(FusedKGOptimizer):
         # all_reduce: their .grad tensors are views into one flat buffer.  The others use the sparse row exchange.
         rows_per_step = self.local_batch_size * (2 + self.neg_sample_size) * self.world
         params = list(self.model.parameters())
-        self._dense = [p for p in params
-                       if p.numel() * p.element_size() <= rows_per_step * ((p.shape[1] if p.dim() > 1 else 1) * p.element_size() + 8)]
+        forced = set()
+        if sparse_exchange:
+            forced = {id(p) for n, p in self.model.named_parameters() if n.split(".")[0] in SPARSE_TABLES}
+        self._dense = [p for p in params if id(p) not in forced and
+                       p.numel() * p.element_size() <= rows_per_step * ((p.shape[1] if p.dim() > 1 else 1) * p.element_size() + 8)]
         self._sparse = [p for p in params if not any(p is d for d in self._dense)]
         if self._dense:
             flat = torch.zeros(sum(p.numel() for p in self._dense), dtype=params[0].dtype, device=params[0].device)
@@ -173,48 +177,58 @@ class FusedDataParallelKGOptimizer(FusedKGOptimizer):
             self._flat_grad = flat
 
     def _step_body(self, batch):
-        """Local forward/backward, then — when every table takes the dense path (no host sync anywhere) — the
-        collectives and the optimizer too, so that the CUDA graph holds the whole step including the two NCCL calls."""
+        """Local forward/backward, the collectives and the optimizer: every shape is static and nothing synchronises
+        with the host, so the CUDA graph holds the whole step including the NCCL calls."""
         self._touched = self._forward_backward(batch)
-        if not self._sparse:
-            self._exchange_and_update()
+        self._exchange_and_update()
 
     def _post_step(self):
-        if self._sparse:
-            self._exchange_and_update()
         for p in self.model.parameters():
             self.optimizer.state[p]["step"] += 1
 
     def _exchange_and_update(self):
         m, opt = self.model, self.optimizer
         heads, rels, tails = self._touched
+        tails = tails.reshape(-1)
         nb = heads.numel()
-        if self.world > 1:                           # one all_gather for every touched row id of every rank
-            ids = torch.cat([heads, rels, tails.reshape(-1)])
-            allids = torch.empty((self.world, ids.numel()), dtype=ids.dtype, device=ids.device)
+        W = self.world
+        if W > 1:                                    # one all_gather for every touched row id of every rank
+            ids = torch.cat([heads, rels, tails])
+            allids = torch.empty((W, ids.numel()), dtype=ids.dtype, device=ids.device)
             dist.all_gather_into_tensor(allids, ids, group=self.pg)
-            heads_all, rels_all, tails_all = (allids[:, :nb].reshape(-1), allids[:, nb:2 * nb].reshape(-1),
-                                              allids[:, 2 * nb:].reshape(-1))
+            heads_all, rels_all, tails_all = allids[:, :nb], allids[:, nb:2 * nb], allids[:, 2 * nb:]
             if self._dense:
                 dist.all_reduce(self._flat_grad, op=dist.ReduceOp.SUM, group=self.pg)
         else:
-            heads_all, rels_all, tails_all = heads, rels, tails.reshape(-1)
-        ent_rows = torch.cat([heads_all, tails_all])
-        zero_row = torch.zeros(1, dtype=torch.int64, device=heads.device)
-        plan = [(m.entity.weight, ent_rows, torch.cat([heads, tails.reshape(-1)])), (m.rel.weight, rels_all, rels),
-                (m.rel_diag.weight, rels_all, rels), (m.c.weight, rels_all if m.multi_c else zero_row, rels if m.multi_c else zero_row)]
+            heads_all, rels_all, tails_all = heads.view(1, -1), rels.view(1, -1), tails.view(1, -1)
+        ent_all = torch.cat([heads_all, tails_all], 1)                   # per rank: [heads | tails], the order of the sent rows
+        zero_row = torch.zeros((1, 1), dtype=torch.int64, device=heads.device)
+        # (table, rows of every rank [W, m_k], this rank's rows)
+        plan = [(m.entity.weight, ent_all, torch.cat([heads, tails])), (m.rel.weight, rels_all, rels),
+                (m.rel_diag.weight, rels_all, rels), (m.c.weight, rels_all if m.multi_c else zero_row, rels if m.multi_c else zero_row.view(-1))]
         if m._ctx_weight() is not None:
             plan.append((m._ctx_weight(), rels_all, rels))
         if m.bias == "learn":
-            plan += [(m.bh.weight, heads_all, heads), (m.bt.weight, tails_all, tails.reshape(-1))]
-        if self.world > 1:
-            for p, _rows_all, rows_local in plan:
-                if any(p is s_ for s_ in self._sparse):
-                    exchange_sparse_rows(p.grad, rows_local, self.pg)                     # big table: only touched rows travel
-                    p.grad.mul_(self.world)                                               # (it averages; we pre-scaled by 1/world)
+            plan += [(m.bh.weight, heads_all, heads), (m.bt.weight, tails_all, tails)]
+        if W > 1 and self._sparse:
+            # Big row-sparse tables (the 4M-entity table and its biases): only the touched rows travel.  Send side:
+            # chk_claim_gather_rows (each row once, cleared locally); one all_gather per table; receive side: the
+            # contributions are added back ONE RANK AT A TIME (a launch holds at most one non-zero contribution per
+            # row), so the sum has the same bits on every replica.
+            recv = []
+            for p, rows_all, rows_local in plan:
+                if not any(p is s_ for s_ in self._sparse):
+                    continue
+                sent = ops.claim_gather_rows(p.grad, rows_local.contiguous(), self._stamps[p], self._step_id)
+                got = torch.empty((W,) + tuple(sent.shape), dtype=sent.dtype, device=sent.device)
+                dist.all_gather_into_tensor(got, sent, group=self.pg)
+                recv.append((p, rows_all, got))
+            for k in range(W):
+                ops.multi_scatter_add([dict(grad=p.grad, rows=rows_all[k].contiguous(), src_rows=got[k]) for p, rows_all, got in recv])
         lr, eps = opt.param_groups[0]["lr"], opt.param_groups[0]["eps"]
-        ops.multi_sparse_adagrad([dict(param=p.data, grad=p.grad, state_sum=opt.state[p]["sum"], rows=rows_all.contiguous(),
-                                       stamp=self._stamps[p]) for p, rows_all, _ in plan], lr, eps, self._step_id)
+        ops.multi_sparse_adagrad([dict(param=p.data, grad=p.grad, state_sum=opt.state[p]["sum"],
+                                       rows=rows_all.reshape(-1).contiguous(), stamp=self._stamps[p]) for p, rows_all, _ in plan],
+                                 lr, eps, self._step_id)
         ops.step_counter_bump(self._step_id)
 
     def step(self, global_batch):

@@ -113,6 +113,14 @@ int chk_nsloss(int dtype, int64_t B, int64_t nt, const void* scores, void* loss_
 int chk_sparse_adagrad(int dtype, void* param, void* grad, void* state_sum, const int64_t* rows, int64_t m,
                        int64_t width, double lr, double eps, int32_t* stamp, const int32_t* step_id, void* stream);
 int chk_step_counter_bump(int32_t* counter, void* stream);
+/* Data-parallel training, send side of the sparse embedding-gradient exchange (the reference has no
+ * distributed code): out_rows[t, :] = the accumulated gradient row rows[t] of the dense `grad` if slot t is the first
+ * slot of this step that names the row, zeros otherwise (so duplicates are sent once); claimed rows of `grad` are
+ * cleared.  stamp / step_id are the ones of chk_sparse_adagrad (a different token is used, call this BEFORE it).
+ * Fixed sizes, no host synchronisation: the ranks all_gather out_rows + rows and add them back rank by rank with
+ * chk_multi_scatter_add, which makes the summed gradient bit-identical on every replica. */
+int chk_claim_gather_rows(int dtype, void* grad, const int64_t* rows, int64_t m, int64_t width, int32_t* stamp,
+                          const int32_t* step_id, void* out_rows, void* stream);
 /* The same two operations over several tables in ONE launch each (entity, rel, rel_diag, context_vec, c, bh, bt):
  *   chk_multi_scatter_add:     grad[rows[i], :] += src_rows[i, :]            (tables with src_rows == NULL are skipped)
  *   chk_multi_sparse_adagrad:  the chk_sparse_adagrad update on rows[0..m) of every table. */

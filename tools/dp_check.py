@@ -92,29 +92,40 @@ def main():
             def get_neg_samples(self, input_batch):
                 return self._negs_static
 
-        ref.load_state_dict(model.state_dict())
-        f1 = FixedF(ref, N3(0.0), torch.optim.Adagrad(ref.parameters(), lr=0.05), B, 1, neg, False, verbose=False)
-        f2 = FixedFDP(model, N3(0.0), torch.optim.Adagrad(model.parameters(), lr=0.05), B, 1, neg, False, verbose=False,
-                      process_group=dist.group.WORLD)
-        f1._negs_static = torch.zeros(B, neg, dtype=torch.int64, device=dev)
-        f2._negs_static = torch.zeros(B // world, neg, dtype=torch.int64, device=dev)
-        for it in range(4):
-            batch = torch.stack([torch.randint(0, n_ent, (B,), generator=g), torch.randint(0, n_rel2, (B,), generator=g),
-                                 torch.randint(0, n_ent, (B,), generator=g)], 1).to(dev)
-            negs = torch.randint(0, n_ent, (B, neg), generator=g).to(dev)
-            f1._negs_static.copy_(negs)
-            f2._negs_static.copy_(negs[rank::world])
-            f1.fused_step(batch)
-            f2.step(batch)
-        worst = 0.0
-        for (k, a), (_, b) in zip(ref.named_parameters(), model.named_parameters()):
-            worst = max(worst, (a.detach() - b.detach()).abs().max().item() / max(a.detach().abs().max().item(), 1e-30))
-        lsum = f2._loss_sum.clone().double()
-        dist.all_reduce(lsum)
-        if rank == 0:
-            print(f"[fused dp {name} r={r} {dtype} x{world}] 4 steps: loss single {f1._loss_sum.item() / 4:.9f} mean-of-ranks "
-                  f"{lsum.item() / world / 4:.9f}  max |param diff| / max|param| = {worst:.2e}", flush=True)
-        assert worst < (1e-9 if dtype == "double" else 5e-3)     # fp32: Adagrad normalises tiny early gradients
+        for sparse in (None, True):              # None: dense all_reduce of the small tables; True: sparse row exchange (big-table path)
+            ref.load_state_dict(model.state_dict())
+            f1 = FixedF(ref, N3(0.0), torch.optim.Adagrad(ref.parameters(), lr=0.05), B, 1, neg, False, verbose=False)
+            f2 = FixedFDP(model, N3(0.0), torch.optim.Adagrad(model.parameters(), lr=0.05), B, 1, neg, False, verbose=False,
+                          process_group=dist.group.WORLD, sparse_exchange=sparse)
+            f1._negs_static = torch.zeros(B, neg, dtype=torch.int64, device=dev)
+            f2._negs_static = torch.zeros(B // world, neg, dtype=torch.int64, device=dev)
+            for it in range(4):
+                batch = torch.stack([torch.randint(0, n_ent, (B,), generator=g), torch.randint(0, n_rel2, (B,), generator=g),
+                                     torch.randint(0, n_ent, (B,), generator=g)], 1)
+                batch[: B // 4, 0] = batch[0, 0]                   # a hot head and a hot tail: rows named by several ranks and
+                batch[: B // 4, 2] = batch[1, 2]                   # several times per rank (claim / duplicate handling)
+                batch = batch.to(dev)
+                negs = torch.randint(0, n_ent, (B, neg), generator=g).to(dev)
+                f1._negs_static.copy_(negs)
+                f2._negs_static.copy_(negs[rank::world])
+                f1.fused_step(batch)
+                f2.step(batch)
+            worst, replica = 0.0, 0.0
+            for (k, a), (_, b) in zip(ref.named_parameters(), model.named_parameters()):
+                worst = max(worst, (a.detach() - b.detach()).abs().max().item() / max(a.detach().abs().max().item(), 1e-30))
+                lo, hi = b.detach().clone(), b.detach().clone()   # replicas must stay BIT-identical
+                dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+                dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+                replica = max(replica, (hi - lo).abs().max().item())
+            lsum = f2._loss_sum.clone().double()
+            dist.all_reduce(lsum)
+            if rank == 0:
+                print(f"[fused dp {name} r={r} {dtype} x{world} {'sparse rows' if sparse else 'dense'}] 4 steps: loss single "
+                      f"{f1._loss_sum.item() / 4:.9f} mean-of-ranks {lsum.item() / world / 4:.9f}  max |param diff| / max|param| = "
+                      f"{worst:.2e}  max replica divergence = {replica:.1e}", flush=True)
+            assert worst < (1e-9 if dtype == "double" else 5e-3)     # fp32: Adagrad normalises tiny early gradients
+            assert replica == 0.0
+            del f1, f2
         model.release_eval_cache()
     dist.barrier()
     if rank == 0:
