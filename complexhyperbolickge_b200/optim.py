@@ -28,6 +28,20 @@ class N3(torch.nn.Module):
         return norm / factors[0].shape[0]
 
 
+class F2(torch.nn.Module):
+    """optimizers/regularizers.py:21-30."""
+
+    def __init__(self, weight: float):
+        super().__init__()
+        self.weight = weight
+
+    def forward(self, factors):
+        norm = 0
+        for f in factors:
+            norm += self.weight * torch.sum(f ** 2)
+        return norm / factors[0].shape[0]
+
+
 class KGOptimizer(object):
     def __init__(self, model, regularizer, optimizer, batch_size, update_steps, neg_sample_size, double_neg,
                  optimizer2=None, loss="crossentropy", smoothing=None, verbose=True):

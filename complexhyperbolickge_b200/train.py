@@ -13,8 +13,10 @@ With ``torch.optim.Adagrad`` (lr_decay = 0, weight_decay = 0) the optimizer step
 ``optimizer.state_dict()`` stays valid); any other optimizer gets the dense ``.grad`` and its own ``step()``.  The
 whole chain has static shapes and is captured in a CUDA graph after the first batch (one graph launch per step; a
 ragged last batch replays eagerly).  The loss is accumulated on the device: one host sync per epoch instead of one
-per step (reference :273 ``l.item()``).  Regularisers with a non-zero weight, gradient accumulation
-(update_steps > 1) and per-negative queries fall back to the unfused contract path of the base class.
+per step (reference :273 ``l.item()``).  The N3 / F2 regularisers (optimizers/regularizers.py:21-58, on the positive
+call's factors entity[h], rel[r], entity[t]) are evaluated in closed form inside the chain: value added to the loss,
+gradient rows 3w|f|f/B (2wf/B) added to the row gradients.  Other regularisers with a non-zero weight and gradient
+accumulation (update_steps > 1) fall back to the unfused contract path of the base class.
 """
 import torch
 
@@ -27,7 +29,11 @@ class FusedKGOptimizer(KGOptimizer):
         super().__init__(*args, **kw)
         m = self.model
         w = getattr(self.regularizer, "weight", None)
-        self.fused = (w == 0 or w == 0.0) and self.update_steps == 1 and m.entity.weight.is_cuda
+        kind = type(self.regularizer).__name__
+        self._reg = None                             # (power, weight) of a closed-form regulariser with non-zero weight
+        if isinstance(w, (int, float)) and w != 0 and kind in ("N3", "F2"):
+            self._reg = (3 if kind == "N3" else 2, float(w))
+        self.fused = (w == 0 or w == 0.0 or self._reg is not None) and self.update_steps == 1 and m.entity.weight.is_cuda
         opt = self.optimizer
         self.sparse_adagrad = (type(opt) is torch.optim.Adagrad and
                                all(g["lr_decay"] == 0 and g["weight_decay"] == 0 and not g.get("maximize", False)
@@ -72,6 +78,21 @@ class FusedKGOptimizer(KGOptimizer):
             g_ent, g_rel, g_rd, g_ctx, g_c = ops.query_bwd(m.KIND, r, bool(m.multi_c), ent, rel, rd, ctx, cw, heads, rels, grad_q)
             tabs = [dict(grad=ent.grad, rows=heads, src_rows=g_ent), dict(grad=rel.grad, rows=rels, src_rows=g_rel),
                     dict(grad=rd.grad, rows=rels, src_rows=g_rd)]
+            if self._reg is not None:                # reg = w * sum_f sum |f|^p / B over (entity[h], rel[r], entity[t])
+                power, w = self._reg
+                pos = batch[:, 2].contiguous()
+                fh, fr, ft = ent[heads], rel[rels], ent[pos]
+                if power == 3:
+                    val = (fh.abs() ** 3).sum() + (fr.abs() ** 3).sum() + (ft.abs() ** 3).sum()
+                    dh, dr, dt = 3 * fh.abs() * fh, 3 * fr.abs() * fr, 3 * ft.abs() * ft
+                else:
+                    val = (fh ** 2).sum() + (fr ** 2).sum() + (ft ** 2).sum()
+                    dh, dr, dt = 2 * fh, 2 * fr, 2 * ft
+                self._loss_sum += val * (w / B)
+                k = w / B * self.grad_scale
+                g_ent.add_(dh, alpha=k)
+                g_rel.add_(dr, alpha=k)
+                tabs.append(dict(grad=ent.grad, rows=pos, src_rows=(dt * k).contiguous()))
             if ctx is not None:
                 tabs.append(dict(grad=ctx.grad, rows=rels, src_rows=g_ctx))
             if m.multi_c:

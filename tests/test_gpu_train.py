@@ -29,10 +29,14 @@ def _feed(cls):
 
 @pytest.mark.parametrize("graph", [False, True])
 @pytest.mark.parametrize("opt_name", ["Adagrad", "Adam"])
-@pytest.mark.parametrize("name,rank,dtype", [("FFTRotH", 33, "double"), ("FFTRefH", 33, "float"), ("FFTAttH", 17, "double"),
-                                            ("FFTRotH", 257, "float")])
-def test_fused_step_matches_contract_path(name, rank, dtype, opt_name, graph):
-    from complexhyperbolickge_b200.optim import KGOptimizer, N3
+@pytest.mark.parametrize("name,rank,dtype,reg", [("FFTRotH", 33, "double", None), ("FFTRefH", 33, "float", None),
+                                                ("FFTAttH", 17, "double", None), ("FFTRotH", 257, "float", None),
+                                                ("FFTRefH", 33, "double", ("N3", 0.05)), ("FFTAttH", 33, "double", ("F2", 0.01)),
+                                                ("FFTRotH", 33, "float", ("N3", 0.05))])
+def test_fused_step_matches_contract_path(name, rank, dtype, reg, opt_name, graph):
+    from complexhyperbolickge_b200 import optim
+    from complexhyperbolickge_b200.optim import KGOptimizer
+    N3 = (lambda _w: getattr(optim, reg[0])(reg[1])) if reg else optim.N3      # regulariser under test (weight 0 by default)
     from complexhyperbolickge_b200.train import FusedKGOptimizer
     B, neg, steps, n_ent, n_rel2 = 48, 21, 5, 700, 10
     a, b = _mk(name, rank, dtype), _mk(name, rank, dtype)
@@ -87,6 +91,8 @@ def test_fused_epoch_runs_and_learns():
     l1 = opt.epoch(ex)
     l2 = opt.epoch(ex)
     assert np.isfinite([l0, l1, l2]).all() and l2 < l0, (l0, l1, l2)
-    # regulariser with a non-zero weight falls back to the contract path
-    opt2 = FusedKGOptimizer(m, N3(0.01), torch.optim.Adagrad(m.parameters(), lr=0.1), 100, 1, 50, False, verbose=False)
+    # gradient accumulation falls back to the contract path; N3 with a non-zero weight stays fused
+    opt2 = FusedKGOptimizer(m, N3(0.01), torch.optim.Adagrad(m.parameters(), lr=0.1), 100, 2, 50, False, verbose=False)
     assert not opt2.fused and np.isfinite(opt2.epoch(ex[:300]))
+    opt3 = FusedKGOptimizer(m, N3(0.01), torch.optim.Adagrad(m.parameters(), lr=0.1), 100, 1, 50, False, verbose=False)
+    assert opt3.fused and np.isfinite(opt3.epoch(ex[:300]))

@@ -100,3 +100,39 @@ def test_shard_bounds_partition():
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
             assert all(lo % 128 == 0 or lo == n for lo, _ in spans)
+
+
+# ---- dataset reader: the reference's pickle format, golden made by the reference itself ----------
+def test_dataset_reader_matches_reference_golden(tmp_path):
+    import pickle as pkl
+    from complexhyperbolickge_b200.datasets import KGDataset, build_filters, write_dataset
+    from complexhyperbolickge_b200.filters import FilterIndex
+    gold_dir = os.path.join(os.path.dirname(__file__), "golden")
+    d = os.path.join(gold_dir, "dataset_toy")
+    exp = np.load(os.path.join(gold_dir, "dataset_toy_expected.npz"))
+    ds = KGDataset(d, False)
+    assert tuple(exp["shape"]) == ds.get_shape()
+    assert np.array_equal(ds.get_examples("train").numpy(), exp["train_examples"])        # reciprocal augmentation
+    assert np.array_equal(ds.get_examples("test").numpy(), exp["test_examples"])
+    assert np.array_equal(ds.get_examples("train", rel_idx=2).numpy(), exp["rel2_examples"])
+    # build_filters == the reference's get_filters (stored in to_skip.pickle by the golden script)
+    allx = np.concatenate([ds.data["train"], ds.data["valid"], ds.data["test"]], 0)
+    lhs, rhs = build_filters(allx, ds.n_predicates // 2)
+    assert lhs == ds.to_skip["lhs"] and rhs == ds.to_skip["rhs"]
+    # write_dataset round trip: byte-compatible content
+    write_dataset(str(tmp_path / "ds"), ds.data["train"], ds.data["valid"], ds.data["test"], ds.n_predicates // 2)
+    ds2 = KGDataset(str(tmp_path / "ds"), False)
+    assert ds2.to_skip == ds.to_skip and np.array_equal(ds2.data["valid"], ds.data["valid"])
+    # CSR form: every evaluated query finds exactly the stored list (plus its own tail)
+    fi = ds.filter_indices()
+    assert isinstance(fi["rhs"], FilterIndex)
+    test = ds.get_examples("test").numpy()
+    indptr, idx = fi["rhs"].batch_csr(test)
+    for i, (h, r, t) in enumerate(test):
+        assert idx[indptr[i]:indptr[i + 1]].tolist() == sorted(set(ds.to_skip["rhs"][(int(h), int(r))]) | {int(t)})
+    lhs_q = np.stack([test[:, 2], test[:, 1] + ds.n_predicates // 2, test[:, 0]], 1)
+    indptr, idx = fi["lhs"].batch_csr(lhs_q)
+    for i, (h, r, t) in enumerate(lhs_q):
+        assert idx[indptr[i]:indptr[i + 1]].tolist() == sorted(set(ds.to_skip["lhs"][(int(h), int(r))]) | {int(t)})
+    with pytest.raises(KeyError):
+        fi["rhs"].batch_csr(np.array([[59, 9, 0]]))
