@@ -121,6 +121,45 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+# ------------------------------------------------------------------------------------------------ watchdog
+class Watchdog:
+    """Per-phase deadlines.  A phase that exceeds its deadline (a hung collective, a rank that lost its GPU, a box that
+    pages for minutes) must not hang the job: every rank dumps its Python stacks to stderr and exits 0; rank 0 first
+    prints the JSON line with whatever has been measured so far plus an "error" key naming the phase."""
+
+    def __init__(self, rank_id):
+        self.rank_id, self.phase, self.deadline, self.partial = rank_id, "start", None, None
+        self.emitted, self.stopped = False, False
+        self.lock = threading.Lock()
+        threading.Thread(target=self._run, daemon=True).start()
+
+    def enter(self, phase, seconds):
+        self.phase, self.deadline = phase, time.time() + seconds
+
+    def stop(self):
+        self.stopped = True
+
+    def emit(self, line):
+        with self.lock:
+            if not self.emitted:
+                self.emitted = True
+                print(json.dumps(line), flush=True)
+
+    def _run(self):
+        import faulthandler
+        while not self.stopped:
+            time.sleep(1.0)
+            if self.deadline is not None and time.time() > self.deadline and not self.stopped:
+                sys.stderr.write(f"[bench watchdog] rank {self.rank_id}: phase '{self.phase}' exceeded its deadline\n")
+                faulthandler.dump_traceback(file=sys.stderr, all_threads=True)
+                sys.stderr.flush()
+                if self.rank_id == 0 and not self.emitted:
+                    line = dict(self.partial) if self.partial else {"metric": METRIC, "value": None, "unit": UNIT}
+                    line["error"] = f"phase '{self.phase}' exceeded its deadline and was abandoned"
+                    self.emit(line)
+                os._exit(0)
+
+
 # ------------------------------------------------------------------------------------------------ CPU arm
 def oracle_eval_sample(model_name, rank, dtype, n_ent, n_rel2, n_queries, ent_slice, seed=0):
     """Time the oracle port's get_ranking on `n_queries` queries against `ent_slice` entity rows and
@@ -268,7 +307,10 @@ def train_big_leg(model, graph, steps, warmup, device, pg, world):
     model.train()
     adagrad = torch.optim.Adagrad(model.parameters(), lr=0.02)
     if world > 1:
-        opt = FusedDataParallelKGOptimizer(model, N3(0.0), adagrad, B, 1, neg, False, verbose=False, process_group=pg)
+        # beyond 2 ranks the step runs eagerly: it is exchange-bound (hundreds of MB of gradient rows per step), so the
+        # ~50 launches cost nothing, and no multi-hundred-MB NCCL collective has to be captured into a CUDA graph
+        opt = FusedDataParallelKGOptimizer(model, N3(0.0), adagrad, B, 1, neg, False, verbose=False, process_group=pg,
+                                           use_cuda_graph=world <= 2)
     else:
         opt = FusedKGOptimizer(model, N3(0.0), adagrad, B, 1, neg, False, verbose=False)
     ex = synthetic.train_examples(graph)
@@ -300,8 +342,9 @@ def train_big_leg(model, graph, steps, warmup, device, pg, world):
     out = {"metric": "train_triples_per_sec", "value": B / (ms * 1e-3), "unit": "triples/s", "ms_per_step": ms,
            "scaling": "weak", "global_batch": B, "mean_loss_rank0": lv,
            "config": f"BASELINE.json configs[4]: FFTRotH rank={rank} Adagrad, 500 triples per rank x{world}, neg={neg}, synthetic 4M-entity "
-                     "graph; fused step (K1 + K3 + loss + adjoints + row-sparse Adagrad, CUDA graph), batch H2D from pinned memory each step"
-                     + ("; replicated tables, sparse gradient-row exchange (claim-gather + all_gather + rank-ordered scatter) inside the graph"
+                     "graph; fused step (K1 + K3 + loss + adjoints + row-sparse Adagrad" + (", CUDA graph" if world <= 2 else ", eager launches")
+                     + "), batch H2D from pinned memory each step"
+                     + ("; replicated tables, sparse gradient-row exchange (claim-gather + all_gather + rank-ordered scatter)"
                         if world > 1 else ""),
            "algorithmic_bytes_per_triple": bytes_per_triple,
            "hbm_frac_per_gpu": B / world / (ms * 1e-3) * bytes_per_triple / 1e9 / 6530.0}
@@ -377,6 +420,8 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py (our arm) needs a CUDA device: complexhyperbolickge_b200 has no CPU fallback")
+    wd = Watchdog(rank_id)
+    wd.enter("setup (NCCL init, synthetic graph, model, evaluation state)", 300)
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     pg = None
@@ -429,6 +474,7 @@ def run_ours(args):
             if world > 1:
                 dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=pg)
 
+        wd.enter("evaluation steps (resident inputs) + roofline probe", 180)
         for i in range(W):
             step(i)
         torch.cuda.synchronize()
@@ -499,6 +545,7 @@ def run_ours(args):
 
     # ---- e2e through the public API with host buffers
     e2e = None
+    wd.enter("end-to-end get_ranking", 120)
     if not args.no_e2e:
         # ONE public-API call over the K timed batches (what compute_metrics does): per batch the host builds the filter
         # CSR, copies ids + CSR host->device from pinned memory and the batch's ranks come back device->host, all
@@ -525,62 +572,76 @@ def run_ours(args):
                "api": f"model.get_ranking(host LongTensor[{K}*{b},3], FilterIndex, batch_size={b}): one call, {K} pipelined "
                       "batches, per batch 1 H2D copy (ids + filter CSR, pinned) and 1 D2H copy (ranks)"}
 
-    dp_train, big_train = None, None
+    # ---- the JSON line so far (rank 0); the training legs below only add keys to it
+    line = None
+    if rank_id == 0:
+        peaks = {}
+        pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(pk):
+            peaks = json.load(open(pk))
+        peak_tf = peaks.get("bf16_tflops", 1590.0)
+        achieved = flops / (kern_ms * 1e-3) / 1e12
+        traffic = None                  # dram bytes per launch of the dominant kernel, from the committed ncu --set full capture
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp) and world == 1 and args.workload == "big4m" and mma:
+            traffic = json.load(open(tp)).get("rank_mma_kernel_big4m_dram_bytes_per_launch")
+        issued = (8 * (rank - 1) * 3 + 8) if mma else 8 * rank
+        roofline = {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                    "traffic": traffic,
+                    "kernel": "rank_mma_kernel<0,0> (tcgen05 bf16x3 contraction + fused epilogue), timed alone with CUDA events recorded "
+                              "around its launch inside chk_rank_counts" if mma else "rank_tile_kernel<float,1> (fp32 FMA)",
+                    "kernel_ms": kern_ms, "call_ms": call_ms,
+                    "call_what": "whole chk_rank_counts call: operand prep + rank_mma_kernel + exact re-check" if mma else "chk_rank_counts",
+                    "call_frac": flops / (call_ms * 1e-3) / 1e12 / peak_tf,
+                    "algorithmic_flop_per_pair": 8 * rank, "issued_flop_per_pair": issued,
+                    "issued_frac": achieved / peak_tf * issued / (8 * rank),
+                    "issued_vs_sustained_peak": (achieved * issued / (8 * rank)) / peaks["bf16_tflops_sustained"] if peaks.get("bf16_tflops_sustained") else None,
+                    "pairs_per_launch": b * shard_rows, "recheck_pairs_per_launch": recheck[0], "recheck_overflow": recheck[1],
+                    "peak_source": ("MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone)" if peaks else "fallback 1.59 PFLOP/s")}
+        line = {"metric": METRIC, "value": b * K / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32" if args.dtype == "float" else "f64", "data": "synthetic", "config": cfg, "clocks": clocks,
+                "e2e": e2e, "gpu_launches": gpu_launches, "roofline": roofline,
+                "mean_rank_check": float(ranks_check.mean())}
+        wd.partial = line
+
+    # ---- training legs (every rank takes part); each has its own deadline, a stuck leg is reported, not waited for
+    del state, ws
+    model.release_eval_cache()
+    torch.cuda.empty_cache()
+    results = {}
     if not args.no_train:
-        model.release_eval_cache()
-        del state, ws
-        torch.cuda.empty_cache()
-        if args.workload == "big4m":
-            big_train = train_big_leg(model, graph, 50, 5, device, pg, world)
-        del model
-        torch.cuda.empty_cache()
-    if world > 1 and not args.no_train:
-        dp_train = dp_train_leg(20, 3, device, pg, world)
-    if rank_id != 0:
         if world > 1:
-            dist.destroy_process_group()
+            wd.enter("data-parallel training leg (configs[1] shape)", 120)
+            results["train"] = dp_train_leg(20, 3, device, pg, world)
+            if line is not None:
+                line.update(results)
+        if args.workload == "big4m":
+            wd.enter("training leg on the 4M-entity table (configs[4])", 180)
+            results["train_big4m"] = train_big_leg(model, graph, 50, 5, device, pg, world)
+            if line is not None:
+                line.update(results)
+    del model
+    torch.cuda.empty_cache()
+    if rank_id != 0:
+        wd.enter("process-group teardown", 30)
+        dist.destroy_process_group()
+        wd.stop()
         return
-    peaks = {}
-    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(pk):
-        peaks = json.load(open(pk))
-    peak_tf = peaks.get("bf16_tflops", 1590.0)
-    achieved = flops / (kern_ms * 1e-3) / 1e12
-    traffic = None                      # dram bytes per launch of the dominant kernel, from the committed ncu --set full capture
-    tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp) and world == 1 and args.workload == "big4m" and mma:
-        traffic = json.load(open(tp)).get("rank_mma_kernel_big4m_dram_bytes_per_launch")
-    issued = (8 * (rank - 1) * 3 + 8) if mma else 8 * rank
-    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                "traffic": traffic,
-                "kernel": "rank_mma_kernel<0,0> (tcgen05 bf16x3 contraction + fused epilogue), timed alone with CUDA events recorded "
-                          "around its launch inside chk_rank_counts" if mma else "rank_tile_kernel<float,1> (fp32 FMA)",
-                "kernel_ms": kern_ms, "call_ms": call_ms,
-                "call_what": "whole chk_rank_counts call: operand prep + rank_mma_kernel + exact re-check" if mma else "chk_rank_counts",
-                "call_frac": flops / (call_ms * 1e-3) / 1e12 / peak_tf,
-                "algorithmic_flop_per_pair": 8 * rank, "issued_flop_per_pair": issued,
-                "issued_frac": achieved / peak_tf * issued / (8 * rank),
-                "pairs_per_launch": b * shard_rows, "recheck_pairs_per_launch": recheck[0], "recheck_overflow": recheck[1],
-                "peak_source": ("MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone)" if peaks else "fallback 1.59 PFLOP/s")}
-    line = {"metric": METRIC, "value": b * K / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f32" if args.dtype == "float" else "f64", "data": "synthetic", "config": cfg, "clocks": clocks,
-            "e2e": e2e, "gpu_launches": gpu_launches, "roofline": roofline,
-            "mean_rank_check": float(ranks_check.mean())}
+    if world == 1 and not args.no_train:
+        wd.enter("single-GPU training leg (configs[1])", 240)
+        line["train"] = train_leg(20, 3, device)
     if world == 1 and not args.no_cpu_baseline:
+        wd.enter("CPU baseline (oracle port on the host cores)", 300)
         v, spent, sample = oracle_eval_budget(model_name, rank, args.dtype, n_ent, n_rel2, budget_s=12.0)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample}
-    if dp_train is not None:
-        line["train"] = dp_train
-    if big_train is not None:
-        line["train_big4m"] = big_train
-    if world == 1 and not args.no_train:
-        line["train"] = train_leg(20, 3, device)
-        if not args.no_cpu_baseline:
+        if not args.no_train:
             line["train"]["cpu_baseline"] = oracle_train_sample()
-    print(json.dumps(line), flush=True)
+    wd.emit(line)
     if world > 1:
+        wd.enter("process-group teardown", 30)
         dist.destroy_process_group()
+    wd.stop()
 
 
 if __name__ == "__main__":

@@ -177,7 +177,13 @@ def rank_queries(model, queries: torch.Tensor, findex: FilterIndex, batch_size: 
                 io["batches"] += 1
 
         one_pass(state, ws)
-        if ws is not None and ops.rank_mma_status(ws)[1]:
+        overflow = ws is not None and ops.rank_mma_status(ws)[1]
+        if state.world > 1 and ws is not None:           # the redo below contains collectives: every rank must agree on it
+            import torch.distributed as dist
+            flag = torch.tensor([int(overflow)], dtype=torch.int32, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=model.process_group)
+            overflow = bool(flag.item())
+        if overflow:
             # the re-check list of some batch overflowed (pathological tie mass): redo the pass on the exact tier
             exact = EvalState.__new__(EvalState)
             exact.__dict__.update(state.__dict__)

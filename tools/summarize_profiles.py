@@ -76,19 +76,22 @@ def main(tag):
     os.makedirs(PR, exist_ok=True)
     agg, tot = launches(tag)
     md = [f"# ncu summaries, round {tag[1:]} (B200, `--clock-control none`)\n",
-          "Source: `gpurun_out/` captures of `python bench.py --steps 2 --warmup 3 --no-cpu-baseline` (launch list) and "
+          "Source: `gpurun_out/` captures of `python bench.py --steps 2 --warmup 3 --no-train --no-cpu-baseline --no-e2e` (launch list: "
+          "setup + 5 evaluation steps + the roofline probe; the same command exited 0 without ncu first) and "
           "`ncu --set full` of single launches; regenerate with `python tools/summarize_profiles.py " + tag + "`.\n",
           "Per-launch times of the launch list are cold-cache and serialised: read SHARES, not absolutes.\n",
-          "## Launch list — top kernels (whole bench run: setup + eval steps + train leg)\n",
+          "## Launch list — top kernels (setup + evaluation steps + roofline probe)\n",
           "| kernel | launches | total ms | avg µs | share |", "|---|---:|---:|---:|---:|"]
     for k, (n, t) in sorted(agg.items(), key=lambda x: -x[1][1])[:16]:
         md.append(f"| `{k}` | {n} | {t / 1e6:.3f} | {t / n / 1e3:.1f} | {100 * t / tot:.1f} % |")
     traffic = {}
-    for name in ("rank_mma", "eval_small", "train"):
+    for name in ("rank_mma", "recheck", "eval_small", "train"):
         if not os.path.exists(os.path.join(GO, f"{tag}_{name}_raw.csv")):
             continue
         md.append(f"\n## `ncu --set full` — {name}\n")
         for d in raw(tag, name):
+            if name == "eval_small" and "recheck_kernel" in d["kernel"]:
+                continue                              # superseded by the dedicated capture of the current re-check kernel
             md.append(f"### `{d['kernel']}`\n")
             md.append("| metric | value | unit |")
             md.append("|---|---:|---|")
@@ -104,9 +107,10 @@ def main(tag):
                 traffic["rank_mma_kernel_big4m_dram_bytes_per_launch"] = num("dram__bytes_read.sum") + num("dram__bytes_write.sum")
                 traffic["rank_mma_kernel_big4m_duration_ms_under_ncu"] = float(d["gpu__time_duration.sum"][0].replace(",", ""))
         shutil.copyfile(os.path.join(GO, f"{tag}_{name}_raw.csv"), os.path.join(PR, f"{tag}_{name}_raw.csv"))
-    src = os.path.join(GO, f"{tag}_rank_mma_source.csv.gz")
-    if os.path.exists(src):
-        shutil.copyfile(src, os.path.join(PR, f"{tag}_rank_mma_source.csv.gz"))
+    for name in ("rank_mma", "recheck"):
+        src = os.path.join(GO, f"{tag}_{name}_source.csv.gz")
+        if os.path.exists(src):
+            shutil.copyfile(src, os.path.join(PR, f"{tag}_{name}_source.csv.gz"))
     open(os.path.join(PR, f"{tag}_summary.md"), "w").write("\n".join(md) + "\n")
     if traffic:
         json.dump(traffic, open(os.path.join(PR, "traffic.json"), "w"), indent=1)
