@@ -136,3 +136,52 @@ def test_dataset_reader_matches_reference_golden(tmp_path):
         assert idx[indptr[i]:indptr[i + 1]].tolist() == sorted(set(ds.to_skip["lhs"][(int(h), int(r))]) | {int(t)})
     with pytest.raises(KeyError):
         fi["rhs"].batch_csr(np.array([[59, 9, 0]]))
+
+
+# ---- bench.py plumbing that needs no GPU ------------------------------------------------------------------------------
+def _load_bench():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("chk_bench_module", os.path.join(ROOT, "bench.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_bench_watchdog_emits_partial_line_and_exits_zero():
+    """A phase that exceeds its deadline must not hang the job: stacks to stderr, the line measured so far + "error" on
+    stdout (rank 0), exit code 0."""
+    import subprocess
+    import sys
+    code = ("import sys, time, importlib.util\n"
+            f"spec = importlib.util.spec_from_file_location('b', r'{os.path.join(ROOT, 'bench.py')}')\n"
+            "m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)\n"
+            "wd = m.Watchdog(int(sys.argv[1])); wd.partial = {'metric': m.METRIC, 'value': 123.0}\n"
+            "wd.enter('fake stuck phase', 1); time.sleep(20); print('NOT REACHED')\n")
+    for rank, expect_line in ((0, True), (3, False)):
+        r = subprocess.run([sys.executable, "-c", code, str(rank)], capture_output=True, text=True, timeout=60)
+        assert r.returncode == 0 and "NOT REACHED" not in r.stdout
+        assert "fake stuck phase" in r.stderr
+        if expect_line:
+            import json
+            line = json.loads(r.stdout.strip())
+            assert line["value"] == 123.0 and "fake stuck phase" in line["error"]
+        else:
+            assert r.stdout.strip() == ""
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """`bench.py --impl reference` (the oracle port on the host cores) on a small workload: one JSON line with the
+    contract's keys; non-zero ranks print nothing."""
+    import json
+    import subprocess
+    import sys
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "wn18rr", "--steps", "1", "--warmup", "0"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, RANK="0"))
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "filtered_eval_queries_per_sec" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
+    assert r.returncode == 0 and r.stdout.strip() == ""
