@@ -9,8 +9,9 @@
  *   - `rank` r: entity rows are 2r wide = [Re X_0..X_{r-1} | Im X_0..X_{r-1}]; n = 2(r-1) must be a
  *     power of two with 16 <= n <= 512 (r in {9,17,33,65,129,257});
  *   - `stream` is a cudaStream_t (the caller's current stream); launches are asynchronous;
- *   - the library never allocates or frees memory it returns, holds no mutable global state besides the
- *     per-thread last-error string, and never calls back into the host language;
+ *   - the library never allocates or frees memory it returns, holds no mutable global state besides per-thread
+ *     items (the last-error string, the measurement events of chk_rank_mma_profile_events) and a cached SM count,
+ *     and never calls back into the host language;
  *   - return value 0 = success, otherwise a CHK_E* code; chk_last_error() gives the text.
  * There is NO CPU fallback: without a CUDA device every compute entry returns CHK_ECUDA.
  */

@@ -96,3 +96,37 @@ def test_fused_epoch_runs_and_learns():
     assert not opt2.fused and np.isfinite(opt2.epoch(ex[:300]))
     opt3 = FusedKGOptimizer(m, N3(0.01), torch.optim.Adagrad(m.parameters(), lr=0.1), 100, 1, 50, False, verbose=False)
     assert opt3.fused and np.isfinite(opt3.epoch(ex[:300]))
+
+
+@pytest.mark.parametrize("dtype,width", [(torch.float32, 66), (torch.float64, 130), (torch.float32, 1)])
+def test_claim_gather_rows_sends_each_row_once(dtype, width):
+    """Send side of the data-parallel sparse exchange (chk_claim_gather_rows): duplicates of a row carry zeros, the
+    claimed rows are cleared in the dense gradient, untouched rows are left alone; claims last for one step."""
+    from complexhyperbolickge_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    N = 50
+    ref = torch.randn(N, width, generator=g).to(dtype).cuda()
+    grad = ref.clone()
+    rows = torch.tensor([3, 7, 3, 49, 7, 7, 0], dtype=torch.int64).cuda()
+    touched = torch.unique(rows)
+    untouched = torch.ones(N, dtype=torch.bool, device="cuda")
+    untouched[touched] = False
+    stamp = torch.zeros(N, dtype=torch.int32, device="cuda")
+    step = torch.ones((), dtype=torch.int32, device="cuda")
+
+    def summed(out):
+        total = torch.zeros_like(ref)
+        total.index_add_(0, rows, out)
+        return total
+
+    out = ops.claim_gather_rows(grad, rows, stamp, step)
+    assert out.shape == (rows.numel(), width)
+    assert torch.equal(summed(out)[touched], ref[touched])            # every distinct row travels exactly once
+    assert torch.equal(grad[untouched], ref[untouched])
+    assert grad[touched].abs().max().item() == 0                      # claimed rows cleared locally
+    grad.copy_(ref)
+    out2 = ops.claim_gather_rows(grad, rows, stamp, step)             # same step: everything is already claimed
+    assert out2.abs().max().item() == 0 and torch.equal(grad, ref)
+    ops.step_counter_bump(step)
+    out3 = ops.claim_gather_rows(grad, rows, stamp, step)             # next step: claims are fresh
+    assert torch.equal(summed(out3)[touched], ref[touched])
