@@ -443,7 +443,9 @@ def run_ours(args):
     n_ent, n_rel2 = graph["n_ent"], graph["n_rel2"]
     margs = Namespace(sizes=(n_ent, n_rel2, n_ent), rank=rank, dropout=0, gamma=0, dtype=args.dtype, bias="learn",
                       init_size=1e-3, multi_c=True)
-    model = getattr(chk, model_name)(margs).to(device)
+    with torch.device(device):          # build the 8.2 GB table ON the GPU: no host copy (8 ranks x 12 GB of host RAM), no CPU init
+        model = getattr(chk, model_name)(margs)
+    model = model.to(device)
     synthetic.trained_like_(model, 0)
     model.eval()
     algo = args.rank_algo
