@@ -220,5 +220,24 @@ def main():
     print("wrote", n, "fixtures to", OUT)
 
 
+def main_high_rank():
+    """Supplement (does not touch the fixtures main() wrote): per-step forward values + autograd gradients of the
+    reference at the ranks of BASELINE.json configs[3..4] (129, 257), fp64, trained-like regime, tiny tables."""
+    os.makedirs(OUT, exist_ok=True)
+    ref_models, _ref_reg, _RefKGOptimizer = ref_shim.load()
+    torch.set_num_threads(4)
+    seed, n = 900, 0
+    for name in MODELS:
+        for rank in (129, 257):
+            seed += 1
+            case = step_case(ref_models, name, "double", True, "trained", rank, 24, 4, 4, 3, seed)
+            np.savez_compressed(os.path.join(OUT, f"step_{name}_double_mc1_trained_r{rank}.npz"), **case)
+            n += 1
+    print("wrote", n, "high-rank fixtures to", OUT)
+
+
 if __name__ == "__main__":
-    main()
+    if "--high-rank" in sys.argv:
+        main_high_rank()
+    else:
+        main()
