@@ -85,10 +85,20 @@ def main(tag):
     for k, (n, t) in sorted(agg.items(), key=lambda x: -x[1][1])[:16]:
         md.append(f"| `{k}` | {n} | {t / 1e6:.3f} | {t / n / 1e3:.1f} | {100 * t / tot:.1f} % |")
     traffic = {}
-    for name in ("rank_mma", "recheck", "eval_small", "train"):
+    for name in ("rank_mma", "recheck", "eval_small", "train", "k1", "k1t"):
         if not os.path.exists(os.path.join(GO, f"{tag}_{name}_raw.csv")):
             continue
         md.append(f"\n## `ncu --set full` — {name}\n")
+        note = {"rank_mma": "Final build of the round (the dominant kernel; `bench.py` workload, one launch).",
+                "recheck": "Final build of the round (whole-row staging, 4 lanes per pair).",
+                "eval_small": "Earlier build of the round: the small kernels around the contraction (K1 at 500 queries, target scores, "
+                              "filter pass); the target / filter kernels have since moved to the re-check kernel's staging.",
+                "train": "Earlier build of the round (before the multi-table scatter / Adagrad launches and the lane-group K3 mapping): "
+                         "kept for the per-kernel picture of the training chain.",
+                "k1": "K1 lane-group kernel, forward and adjoint, at 2^20 queries (`tools/k1_profile_case.py`).",
+                "k1t": "K1 thread-per-query variant at 2^20 queries, ungrouped input (`tools/k1_profile_case.py`)."}.get(name)
+        if note:
+            md.append(note + "\n")
         for d in raw(tag, name):
             if name == "eval_small" and "recheck_kernel" in d["kernel"]:
                 continue                              # superseded by the dedicated capture of the current re-check kernel
@@ -107,7 +117,7 @@ def main(tag):
                 traffic["rank_mma_kernel_big4m_dram_bytes_per_launch"] = num("dram__bytes_read.sum") + num("dram__bytes_write.sum")
                 traffic["rank_mma_kernel_big4m_duration_ms_under_ncu"] = float(d["gpu__time_duration.sum"][0].replace(",", ""))
         shutil.copyfile(os.path.join(GO, f"{tag}_{name}_raw.csv"), os.path.join(PR, f"{tag}_{name}_raw.csv"))
-    for name in ("rank_mma", "recheck"):
+    for name in ("rank_mma", "recheck", "k1", "k1t"):
         src = os.path.join(GO, f"{tag}_{name}_source.csv.gz")
         if os.path.exists(src):
             shutil.copyfile(src, os.path.join(PR, f"{tag}_{name}_source.csv.gz"))
