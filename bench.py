@@ -617,18 +617,24 @@ def run_ours(args):
     del state, ws
     model.release_eval_cache()
     torch.cuda.empty_cache()
-    results = {}
+    def leg(key, what, seconds, fn, *a):
+        """A training leg adds a key to the line; if it fails the headline (evaluation) numbers are still reported."""
+        import traceback
+        wd.enter(what, seconds)
+        try:
+            out = fn(*a)
+        except Exception as e:                       # noqa: BLE001 — reported in the line, stack on stderr
+            traceback.print_exc(file=sys.stderr)
+            out = {"error": f"{type(e).__name__}: {e}"[:400]}
+        if line is not None:
+            line[key] = out
+
     if not args.no_train:
         if world > 1:
-            wd.enter("data-parallel training leg (configs[1] shape)", 120)
-            results["train"] = dp_train_leg(20, 3, device, pg, world)
-            if line is not None:
-                line.update(results)
+            leg("train", "data-parallel training leg (configs[1] shape)", 120, dp_train_leg, 20, 3, device, pg, world)
         if args.workload == "big4m":
-            wd.enter("training leg on the 4M-entity table (configs[4])", 180)
-            results["train_big4m"] = train_big_leg(model, graph, 50, 5, device, pg, world)
-            if line is not None:
-                line.update(results)
+            leg("train_big4m", "training leg on the 4M-entity table (configs[4])", 180, train_big_leg, model, graph, 50, 5,
+                device, pg, world)
     del model
     torch.cuda.empty_cache()
     if rank_id != 0:
@@ -637,13 +643,12 @@ def run_ours(args):
         wd.stop()
         return
     if world == 1 and not args.no_train:
-        wd.enter("single-GPU training leg (configs[1])", 240)
-        line["train"] = train_leg(20, 3, device)
+        leg("train", "single-GPU training leg (configs[1])", 240, train_leg, 20, 3, device)
     if world == 1 and not args.no_cpu_baseline:
         wd.enter("CPU baseline (oracle port on the host cores)", 300)
         v, spent, sample = oracle_eval_budget(model_name, rank, args.dtype, n_ent, n_rel2, budget_s=12.0)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample}
-        if not args.no_train:
+        if not args.no_train and "error" not in line.get("train", {"error": 1}):
             line["train"]["cpu_baseline"] = oracle_train_sample()
     wd.emit(line)
     if world > 1:
