@@ -58,32 +58,32 @@ class KGDataset(object):
     """datasets/kg_dataset.py:18-73 (same constructor, attributes and methods)."""
 
     def __init__(self, data_path, debug=False):
-        self.data_path = data_path
-        self.debug = debug
-        self.data = {}
-        for split in ["train", "test", "valid"]:
-            with open(os.path.join(self.data_path, split + ".pickle"), "rb") as in_file:
-                self.data[split] = pkl.load(in_file)
-        with open(os.path.join(self.data_path, "to_skip.pickle"), "rb") as filters_file:
-            self.to_skip = pkl.load(filters_file)
-        max_axis = np.max(self.data["train"], axis=0)
-        self.n_entities = int(max(max_axis[0], max_axis[2]) + 1)
-        self.n_predicates = int(max_axis[1] + 1) * 2
+        self.data_path, self.debug = data_path, debug
+
+        def unpickle(stem):
+            with open(os.path.join(data_path, stem + ".pickle"), "rb") as fh:
+                return pkl.load(fh)
+
+        self.data = {split: unpickle(split) for split in ("train", "test", "valid")}
+        self.to_skip = unpickle("to_skip")
+        top = self.data["train"].max(axis=0)                 # the shape is inferred from the training split (:39-41)
+        self.n_entities = int(max(top[0], top[2])) + 1
+        self.n_predicates = 2 * (int(top[1]) + 1)            # reciprocal relations included
         self._findex = None
 
     def get_examples(self, split, rel_idx=-1):
-        """Triples of a split; the training split gets the reciprocal triples (rhs, rel + R, lhs) appended (:54-60)."""
-        examples = self.data[split]
+        """Triples of a split as int64 [n, 3]; the training split gets the reciprocal triples
+        (rhs, rel + R, lhs) appended (:54-60); rel_idx >= 0 keeps one relation; debug keeps the first 1000."""
+        triples = np.asarray(self.data[split])
         if split == "train":
-            inv = np.copy(examples)
-            inv[:, 0], inv[:, 2] = examples[:, 2], examples[:, 0]
-            inv[:, 1] += self.n_predicates // 2
-            examples = np.vstack((examples, inv))
+            flipped = triples[:, ::-1].copy()
+            flipped[:, 1] += self.n_predicates // 2
+            triples = np.concatenate([triples, flipped], axis=0)
         if rel_idx >= 0:
-            examples = examples[examples[:, 1] == rel_idx]
+            triples = triples[triples[:, 1] == rel_idx]
         if self.debug:
-            examples = examples[:1000]
-        return torch.from_numpy(examples.astype("int64"))
+            triples = triples[:1000]
+        return torch.from_numpy(np.ascontiguousarray(triples, dtype=np.int64))
 
     def get_filters(self):
         """The reference's dict-of-lists (:67-69); get_ranking/compute_metrics accept it as is."""
