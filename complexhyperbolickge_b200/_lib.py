@@ -26,6 +26,28 @@ class TableDesc(ctypes.Structure):
                 ("width", _i64), ("stamp", _p)]
 
 
+CHK_OPT_NONE, CHK_OPT_ADAGRAD, CHK_OPT_ADAM = 0, 1, 2
+CHK_HYPER_LEN = 8
+CHK_RED_MAX_COLS, CHK_RED_MAX_GROUPS = 4, 3
+
+
+class RedCol(ctypes.Structure):
+    """chk_red_col of include/chk_b200.h."""
+    _fields_ = [("param", _p), ("state0", _p), ("dense_grad", _p), ("width", _i64), ("src", _p * 2), ("lo", _i64 * 2),
+                ("hi", _i64 * 2), ("rank_stride", _i64 * 2)]
+
+
+class RedGroup(ctypes.Structure):
+    """chk_red_group of include/chk_b200.h."""
+    _fields_ = [("ids", _p), ("n_keys", _i64), ("slots_per_rank", _i64), ("world", ctypes.c_int32), ("n_cols", ctypes.c_int32),
+                ("single_row", ctypes.c_int32), ("pad_", ctypes.c_int32), ("work", _p), ("cols", RedCol * CHK_RED_MAX_COLS)]
+
+
+class DenseTab(ctypes.Structure):
+    """chk_dense_tab of include/chk_b200.h."""
+    _fields_ = [("param", _p), ("grad", _p), ("state0", _p), ("state1", _p), ("n", _i64)]
+
+
 # name -> (restype, argtypes); mirrors include/chk_b200.h line by line
 SIGNATURES = {
     "chk_abi_version": (_i, []),
@@ -44,6 +66,16 @@ SIGNATURES = {
     "chk_multi_scatter_add": (_i, [_i, ctypes.POINTER(TableDesc), _i, _p]),
     "chk_multi_sparse_adagrad": (_i, [_i, ctypes.POINTER(TableDesc), _i, ctypes.c_double, ctypes.c_double, _p, _p]),
     "chk_scatter_add_rows": (_i, [_i, _p, _p, _p, _i64, _i64, _p]),
+    "chk_train_prep": (_i, [_p, _i64, _i64, _i64, _i, _p, _p, ctypes.c_uint64, _p, ctypes.c_uint32, _p, _p, _p, _p]),
+    "chk_score_gather_train": (_i, [_i, _i, _i64, _i64, _p, _i64, _i64, _p, _p, _p, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "chk_group_workspace_bytes": (_i64, [_i64, _i64]),
+    "chk_group_build": (_i, [_p, _i64, _i64, _p, _p]),
+    "chk_reduce_apply": (_i, [_i, _i, ctypes.POINTER(RedGroup), _i, _p, _p]),
+    "chk_step_finish": (_i, [_i, ctypes.POINTER(_p), _i, _p, _i64, _p, _p, _p]),
+    "chk_dense_apply": (_i, [_i, _i, ctypes.POINTER(DenseTab), _i, _p, _p, _p]),
+    "chk_rowsum_groups": (_i, [_i, _p, _i64, _i64, _i64, _p, _p]),
+    "chk_reg_factors": (_i, [_i, _i, ctypes.c_double, _p, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _p, _i64, _p, _i64, _p, _i64,
+                             _p, _i64, _p, _p]),
     "chk_row_hnorm": (_i, [_i, _i, _i64, _p, _p, _p]),
     "chk_score_all": (_i, [_i, _i, _i64, _p, _p, _p, _p, _p, _p, _i64, _p, _p]),
     "chk_target_scores": (_i, [_i, _i, _i64, _p, _p, _p, _p, _p, _p, _p, _p]),

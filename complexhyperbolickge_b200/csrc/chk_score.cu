@@ -23,7 +23,18 @@ template <typename T> struct SArgs {
     T* scores;                       // fwd
     const T* grad_scores; T* grad_q; T* grad_rows;   // bwd
     T* grad_dense;                   // bwd, optional: accumulate tail-row gradients straight into the dense table gradient
+    // MODE 2 (training: forward + negative-sampling loss + backward in one pass, chk_score_gather_train)
+    const int64_t* head_idx; int64_t head_stride_b, head_stride_j; const T* bh_table;   // bh value of pair (b,j) = bh_table[head_idx[..]]
+    const double* hyper;             // device scalars: [2] = 1/(number of loss terms of the GLOBAL batch), [3] = valid rows of this batch
+    T* loss_part;                    // [B] per-row loss partial (already scaled by hyper[2])
+    T* gscores;                      // [B, nt] d loss / d score (feeds the bt gradient); g_bh[b] = sum_j of it
+    T* g_bh;                         // [B] (one query per row) or NULL (per-pair queries: the bh gradient of a pair is gscores itself)
 };
+
+template <typename T>
+__device__ __forceinline__ T logsigmoid_t(T x) {          // min(x,0) - log1p(exp(-|x|)), as ATen
+    return Sc<T>::min_(x, T(0)) - Sc<T>::log1p_(Sc<T>::exp_(-Sc<T>::abs_(x)));
+}
 
 // A group of L = 2^LOGL lanes owns one (query, tail) pair: lane gl of the group holds complex coefficients
 // k = gl, gl+L, ... (P per lane), so a warp works on 32/L pairs at once and the per-pair scalar section
@@ -53,17 +64,25 @@ __device__ __forceinline__ void group_sum3(T& a, T& b, T& c) {
     }
 }
 
-template <typename T, int LOGL, int P, bool BWD>
+// MODE 0: scores; MODE 1: adjoint from given d/dscores; MODE 2: training pass — scores, the negative-sampling loss terms
+// -logsigmoid(+s) (column 0) / -logsigmoid(-s) (columns >= 1) of KGOptimizer.neg_sampling_loss (reference
+// optimizers/kg_optimizer.py:115-122), their derivative and the adjoint, with every tail row gathered ONCE.
+template <typename T, int LOGL, int P, int MODE>
 __global__ void __launch_bounds__(kWarps * 32) score_gather_kernel(SArgs<T> A) {
+    constexpr bool BWD = MODE >= 1, TRAIN = MODE == 2;
     constexpr int L = 1 << LOGL, G = 32 / L;          // lanes per pair, pairs per warp
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gl = lane & (L - 1), grp = lane >> LOGL;
     const int r = A.r;
     extern __shared__ unsigned char smem_raw[];
     T* red = reinterpret_cast<T*>(smem_raw);          // [kWarps][2r] for the grad_q reduction (BWD)
+    __shared__ T red2[2][kWarps];                     // TRAIN: per-warp loss / bh-gradient partials
+    T inv_total = T(0); int64_t n_valid = A.B;
+    if (TRAIN) { inv_total = (T)A.hyper[2]; n_valid = (int64_t)A.hyper[3]; }
     for (int64_t b = blockIdx.x; b < A.B; b += gridDim.x) {
         T zr[P], zi[P], gzr[P], gzi[P];
         T zn = T(0);
+        T loss_acc = T(0), gbh_acc = T(0);            // TRAIN: held by the gl == 0 lane of every pair group
         const bool per_pair_q = A.q_stride_j != 0;
         if (!per_pair_q) {
             load_row<T, LOGL, P>(A.q + b * A.q_stride_b * 2 * r, r, gl, zr, zi);
@@ -101,7 +120,23 @@ __global__ void __launch_bounds__(kWarps * 32) score_gather_kernel(SArgs<T> A) {
                     A.scores[pair] = A.bt ? Sc<T>::add_(Sc<T>::add_(A.bh_vals[b * A.bh_stride_b + j * A.bh_stride_j], A.bt[row]), s) : s;
                 }
             } else {
-                const T gd = valid ? T(-2) * d * A.grad_scores[pair] : T(0);
+                T gsc;
+                if (TRAIN) {
+                    T s = -Sc<T>::mul_(d, d);
+                    if (A.bt) s = Sc<T>::add_(Sc<T>::add_(A.bh_table[A.head_idx[b * A.head_stride_b + j * A.head_stride_j]], A.bt[row]), s);
+                    const bool pos = j == 0;
+                    const T xs = pos ? s : -s;                               // term = -logsigmoid(xs)
+                    const bool live = valid && b < n_valid;                 // padding rows of a ragged batch carry no loss
+                    const T gterm = -(T(1) / (T(1) + Sc<T>::exp_(xs))) * inv_total;   // d(-logsigmoid(xs))/dxs / total = -sigmoid(-xs)/total
+                    gsc = live ? (pos ? gterm : -gterm) : T(0);
+                    if (gl == 0 && valid) {
+                        A.gscores[pair] = gsc;
+                        if (live) { loss_acc -= logsigmoid_t<T>(xs) * inv_total; gbh_acc += gsc; }
+                    }
+                } else {
+                    gsc = valid ? A.grad_scores[pair] : T(0);
+                }
+                const T gd = T(-2) * d * gsc;
                 const T re1 = re - T(1);
                 const T mod2 = Sc<T>::fma_(re1, re1, im * im);
                 const T sq = Sc<T>::sqrt_(x * x - T(1));
@@ -147,6 +182,20 @@ __global__ void __launch_bounds__(kWarps * 32) score_gather_kernel(SArgs<T> A) {
                 }
             }
         }
+        if (TRAIN) {
+            // fixed-order block reduction of the row's loss terms and bh gradient (bit-reproducible: no atomics)
+            loss_acc = warp_sum<T>(loss_acc); gbh_acc = warp_sum<T>(gbh_acc);
+            __syncthreads();
+            if (lane == 0) { red2[0][warp] = loss_acc; red2[1][warp] = gbh_acc; }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                T l = T(0), g = T(0);
+#pragma unroll
+                for (int w = 0; w < kWarps; ++w) { l += red2[0][w]; g += red2[1][w]; }
+                A.loss_part[b] = l;
+                if (A.g_bh) A.g_bh[b] = g;
+            }
+        }
         if (BWD && !per_pair_q) {
             // sum the per-lane partial gradients over the warp's pair groups, then over the warps
 #pragma unroll
@@ -176,12 +225,13 @@ __global__ void __launch_bounds__(kWarps * 32) score_gather_kernel(SArgs<T> A) {
     }
 }
 
-template <typename T, bool BWD>
+template <typename T, int MODE>
 int launch_gather(const SArgs<T>& A, cudaStream_t st) {
+    constexpr bool BWD = MODE >= 1;
     int64_t blocks = A.B < 148 * 32 ? A.B : 148 * 32;
     size_t smem = BWD ? (size_t)kWarps * 2 * A.r * sizeof(T) : 0;
 #define CHK_LAUNCH(LOGL, P)                                                                         \
-    score_gather_kernel<T, LOGL, P, BWD><<<(unsigned)blocks, kWarps * 32, smem, st>>>(A)
+    score_gather_kernel<T, LOGL, P, MODE><<<(unsigned)blocks, kWarps * 32, smem, st>>>(A)
     const int r = A.r;
     if (r <= 10) CHK_LAUNCH(1, 5);            // rank 9:   2 lanes x 5
     else if (r <= 20) CHK_LAUNCH(2, 5);       // rank 17:  4 lanes x 5
@@ -219,11 +269,11 @@ extern "C" int chk_score_gather_fwd(int dtype, int rank, int64_t B, int64_t nt,
     if (dtype == CHK_F32) {
         SArgs<float> A{(const float*)q, q_stride_b, q_stride_j, (const float*)table, tail_idx, row_stride_b,
                        (const float*)bh_vals, bh_stride_b, bh_stride_j, (const float*)bt, B, nt, rank, (float*)scores, nullptr, nullptr, nullptr, nullptr};
-        return launch_gather<float, false>(A, st);
+        return launch_gather<float, 0>(A, st);
     } else if (dtype == CHK_F64) {
         SArgs<double> A{(const double*)q, q_stride_b, q_stride_j, (const double*)table, tail_idx, row_stride_b,
                         (const double*)bh_vals, bh_stride_b, bh_stride_j, (const double*)bt, B, nt, rank, (double*)scores, nullptr, nullptr, nullptr, nullptr};
-        return launch_gather<double, false>(A, st);
+        return launch_gather<double, 0>(A, st);
     }
     chk_set_error("unknown dtype %d", dtype); return CHK_EINVAL;
 }
@@ -241,11 +291,11 @@ static int score_gather_bwd_impl(int dtype, int rank, int64_t B, int64_t nt,
     if (dtype == CHK_F32) {
         SArgs<float> A{(const float*)q, q_stride_b, q_stride_j, (const float*)table, tail_idx, row_stride_b,
                        nullptr, 0, 0, nullptr, B, nt, rank, nullptr, (const float*)grad_scores, (float*)grad_q, (float*)grad_rows, (float*)grad_dense};
-        return launch_gather<float, true>(A, st);
+        return launch_gather<float, 1>(A, st);
     } else if (dtype == CHK_F64) {
         SArgs<double> A{(const double*)q, q_stride_b, q_stride_j, (const double*)table, tail_idx, row_stride_b,
                         nullptr, 0, 0, nullptr, B, nt, rank, nullptr, (const double*)grad_scores, (double*)grad_q, (double*)grad_rows, (double*)grad_dense};
-        return launch_gather<double, true>(A, st);
+        return launch_gather<double, 1>(A, st);
     }
     chk_set_error("unknown dtype %d", dtype); return CHK_EINVAL;
 }
@@ -279,4 +329,39 @@ extern "C" int chk_scatter_add_rows(int dtype, void* dense, const int64_t* idx, 
     else { chk_set_error("unknown dtype %d", dtype); return CHK_EINVAL; }
     CHK_CUDA_LAUNCH_CHECK("scatter_add_rows_kernel");
     return CHK_OK;
+}
+
+// Training pass (MODE 2): replaces, for one batch, the two model() calls of KGOptimizer.neg_sampling_loss plus
+// F.logsigmoid / mean and their autograd backward (reference optimizers/kg_optimizer.py:101-123) — see the header.
+template <typename T>
+static int score_gather_train_t(int rank, int64_t B, int64_t nt, const void* q, int64_t q_stride_b, int64_t q_stride_j,
+                                const void* table, const int64_t* tail_idx, const int64_t* head_idx, int64_t head_stride_b,
+                                int64_t head_stride_j, const void* bh, const void* bt, const double* hyper, void* loss_part,
+                                void* grad_scores, void* grad_q, void* grad_rows, void* g_bh, cudaStream_t st) {
+    SArgs<T> A{};
+    A.q = (const T*)q; A.q_stride_b = q_stride_b; A.q_stride_j = q_stride_j;
+    A.table = (const T*)table; A.tail_idx = tail_idx; A.row_stride_b = 0;
+    A.bt = (const T*)bt; A.B = B; A.nt = nt; A.r = rank;
+    A.grad_q = (T*)grad_q; A.grad_rows = (T*)grad_rows; A.grad_dense = nullptr;
+    A.head_idx = head_idx; A.head_stride_b = head_stride_b; A.head_stride_j = head_stride_j; A.bh_table = (const T*)bh;
+    A.hyper = hyper; A.loss_part = (T*)loss_part; A.gscores = (T*)grad_scores; A.g_bh = (T*)g_bh;
+    return launch_gather<T, 2>(A, st);
+}
+
+extern "C" int chk_score_gather_train(int dtype, int rank, int64_t B, int64_t nt,
+                                      const void* q, int64_t q_stride_b, int64_t q_stride_j,
+                                      const void* table, const int64_t* tail_idx,
+                                      const int64_t* head_idx, int64_t head_stride_b, int64_t head_stride_j,
+                                      const void* bh, const void* bt, const double* hyper,
+                                      void* loss_part, void* grad_scores, void* grad_q, void* grad_rows, void* g_bh,
+                                      void* stream) {
+    if (B == 0 || nt == 0) return CHK_OK;
+    if (B < 0 || nt < 0 || rank < 2 || !q || !table || !tail_idx || !hyper || !loss_part || !grad_scores || !grad_q || !grad_rows ||
+        ((bh == nullptr) != (bt == nullptr)) || (bh && !head_idx)) {
+        chk_set_error("chk_score_gather_train: bad argument"); return CHK_EINVAL;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == CHK_F32) return score_gather_train_t<float>(rank, B, nt, q, q_stride_b, q_stride_j, table, tail_idx, head_idx, head_stride_b, head_stride_j, bh, bt, hyper, loss_part, grad_scores, grad_q, grad_rows, g_bh, st);
+    if (dtype == CHK_F64) return score_gather_train_t<double>(rank, B, nt, q, q_stride_b, q_stride_j, table, tail_idx, head_idx, head_stride_b, head_stride_j, bh, bt, hyper, loss_part, grad_scores, grad_q, grad_rows, g_bh, st);
+    chk_set_error("unknown dtype %d", dtype); return CHK_EINVAL;
 }

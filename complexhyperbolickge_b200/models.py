@@ -131,9 +131,10 @@ class FFTUnitBall(KGModel):
             nn.init.uniform_(self.rel_diag.weight, -1.0, 1.0)
             nn.init.ones_(self.c.weight)
         self.lift = True
-        self.rank_algo = "fma"           # "fma" | "mma" (fp32 tcgen05 tier)
+        self.rank_algo = "auto"          # "auto" (tcgen05 tier when the table is large enough to pay for the shadow) | "fma" | "mma"
+        self._param_epoch = 0            # bumped by optimizers that write parameters through raw pointers (train.py, parallel.py)
         self.process_group = None        # set to shard the entity table across ranks in get_ranking
-        self._filter_cache: Dict[int, FilterIndex] = {}
+        self._filter_cache: Dict[int, tuple] = {}
         self._eval_cache = None          # (key, ranking.EvalState): shard view, Hermitian norms, bf16 shadow
         self._eval_ws = None
         self.fused_forward = True
@@ -200,9 +201,12 @@ class FFTUnitBall(KGModel):
             return filters
         key = id(filters)
         hit = self._filter_cache.get(key)
-        if hit is None or hit[0] != len(filters):
-            self._filter_cache[key] = (len(filters), FilterIndex.from_dict(filters, self.sizes[1]))
-        return self._filter_cache[key][1]
+        # the entry keeps the dict alive, so its id cannot be recycled for another dict while it is cached
+        if hit is None or hit[0] is not filters or hit[1] != len(filters):
+            if len(self._filter_cache) >= 4:                     # rhs/lhs of valid + test; bounded
+                self._filter_cache.pop(next(iter(self._filter_cache)))
+            hit = self._filter_cache[key] = (filters, len(filters), FilterIndex.from_dict(filters, self.sizes[1]))
+        return hit[2]
 
     def get_ranking(self, queries, filters, batch_size=500):
         """Filtered ranks of the true tails (models/base.py:228-280), float32 CPU tensor [n].
@@ -215,6 +219,18 @@ class FFTUnitBall(KGModel):
         if isinstance(queries, np.ndarray):
             queries = torch.from_numpy(queries)
         return rank_queries(self, queries, self._filter_index(filters), batch_size)
+
+    def parameters_changed(self):
+        """Tell the model its tables were written through raw device pointers (no torch ``_version`` bump): the cached
+        evaluation state (Hermitian norms, bf16 shadow) is stale.  The fused optimizers call this after every step."""
+        self._param_epoch += 1
+
+    def resolved_rank_algo(self) -> str:
+        """"auto": the tcgen05 tier when it is built and the table is big enough that the contraction, not the per-batch
+        prologue, dominates (N >= 8192 rows; below that the exact FMA tier finishes a 500-query batch in < 0.1 ms)."""
+        if self.rank_algo != "auto":
+            return self.rank_algo
+        return "mma" if (self.sizes[0] >= 8192 and ops.mma_available(self.rank)) else "fma"
 
     def release_eval_cache(self):
         """Drop the cached evaluation state (entity shadow, norms, workspace) to give the memory back."""

@@ -56,13 +56,17 @@ def supported_rank(rank: int) -> bool:
 GROUPED_MIN_QUERIES = 1 << 16      # from here on the thread-per-query K1 (+ argsort by relation) beats the lane-group kernel
 
 
-def query_fwd(kind, rank, multi_c, entity, rel, rel_diag, ctx, c_table, head_idx, rel_idx, grouped=None):
+def query_fwd(kind, rank, multi_c, entity, rel, rel_diag, ctx, c_table, head_idx, rel_idx, grouped=None, out=None):
     """get_queries.  grouped=None picks the throughput variant (chk_query_fwd_grouped, queries processed in relation
-    order) for large fp32 batches at rank <= 33; True / False force it."""
+    order) for large fp32 batches at rank <= 33; True / False force it.  out = (q, c) preallocated outputs."""
     _chk(entity, rel, rel_diag, ctx, c_table, head_idx, rel_idx)
     nq = head_idx.numel()
-    q = torch.empty((nq, 2 * rank), dtype=entity.dtype, device=entity.device)
-    c = torch.empty((nq,), dtype=entity.dtype, device=entity.device)
+    if out is not None:
+        q, c = out
+        _chk(q, c)
+    else:
+        q = torch.empty((nq, 2 * rank), dtype=entity.dtype, device=entity.device)
+        c = torch.empty((nq,), dtype=entity.dtype, device=entity.device)
     can_group = entity.dtype == torch.float32 and rank in (9, 17, 33)
     if grouped is None:
         grouped = can_group and nq >= GROUPED_MIN_QUERIES
@@ -451,3 +455,117 @@ class FusedForwardFn(torch.autograd.Function):
             scatter_add_rows(g_bt, tails.view(-1), g)
         return (None, grads["entity"], grads["rel"], grads["rel_diag"], grads.get("context_vec"), grads["c"], g_bh,
                 g_bt, None, None)
+
+
+# ------------------------------------------------------------------------------------------- fused training step
+from ._lib import CHK_HYPER_LEN, CHK_OPT_ADAGRAD, CHK_OPT_ADAM, CHK_OPT_NONE  # noqa: E402,F401
+
+
+def train_prep(batch, neg, n_entities, double_neg, seed, step_id, stream_id, heads, rels, tails, injected_tails=None,
+               injected_heads=None):
+    """Device sampler + id arrays of one step (chk_train_prep); heads / rels / tails are preallocated int64 outputs."""
+    _chk(batch, step_id, heads, rels, tails, injected_tails, injected_heads)
+    B = batch.shape[0]
+    _lib.check(_lib.lib().chk_train_prep(_p(batch), B, neg, n_entities, int(double_neg), _p(injected_tails), _p(injected_heads),
+                                         int(seed) & 0xFFFFFFFFFFFFFFFF, _p(step_id), int(stream_id) & 0xFFFFFFFF, _p(heads), _p(rels),
+                                         _p(tails), _stream()), "chk_train_prep")
+    _launched(1)
+
+
+def score_gather_train(rank, B, nt, q, q_stride_b, q_stride_j, table, tail_idx, head_idx, head_stride_b, head_stride_j, bh, bt,
+                       hyper, loss_part, grad_scores, grad_q, grad_rows, g_bh):
+    """K3 training pass: scores + negative-sampling loss terms + adjoint (all outputs preallocated)."""
+    _chk(q, table, tail_idx, head_idx, bh, bt, hyper, loss_part, grad_scores, grad_q, grad_rows, g_bh)
+    _lib.check(_lib.lib().chk_score_gather_train(_dt(q), rank, B, nt, _p(q), q_stride_b, q_stride_j, _p(table), _p(tail_idx),
+                                                 _p(head_idx), head_stride_b, head_stride_j, _p(bh), _p(bt), _p(hyper),
+                                                 _p(loss_part), _p(grad_scores), _p(grad_q), _p(grad_rows), _p(g_bh), _stream()),
+               "chk_score_gather_train")
+    _launched(1)
+
+
+def query_bwd_into(kind, rank, multi_c, entity, rel, rel_diag, ctx, c_table, head_idx, rel_idx, grad_q, g_ent, g_rel, g_rd, g_ctx,
+                   g_c):
+    """chk_query_bwd into preallocated gradient-row buffers."""
+    _chk(entity, rel, rel_diag, ctx, c_table, head_idx, rel_idx, grad_q, g_ent, g_rel, g_rd, g_ctx, g_c)
+    _lib.check(_lib.lib().chk_query_bwd(kind, _dt(entity), rank, head_idx.numel(), int(multi_c), _p(entity), _p(rel), _p(rel_diag),
+                                        _p(ctx), _p(c_table), _p(head_idx), _p(rel_idx), _p(grad_q), _p(g_ent), _p(g_rel), _p(g_rd),
+                                        _p(g_ctx), _p(g_c), _stream()), "chk_query_bwd")
+    _launched(1)
+
+
+def group_workspace(n_keys, total_slots, device):
+    """Zero-initialised int32 workspace of chk_group_build for a key space of n_keys rows and total_slots slots."""
+    nbytes = _lib.lib().chk_group_workspace_bytes(n_keys, total_slots)
+    if nbytes <= 0:
+        raise RuntimeError(f"chk_group_workspace_bytes({n_keys}, {total_slots}) failed")
+    return torch.zeros((nbytes // 4,), dtype=torch.int32, device=device)
+
+
+def group_build(ids, n_keys, work):
+    _chk(ids, work)
+    _lib.check(_lib.lib().chk_group_build(_p(ids), ids.numel(), n_keys, _p(work), _stream()), "chk_group_build")
+    _launched(3)
+
+
+def _red_groups(groups):
+    """groups: list of dicts(ids=, n_keys=, slots_per_rank=, world=, work=, single_row=, cols=[dict(param=, state0=, dense=,
+    src=[(tensor, lo, hi, rank_stride), ...])]); tensors are kept alive by the caller."""
+    arr = (_lib.RedGroup * len(groups))()
+    for G, g in zip(arr, groups):
+        _chk(g.get("ids"), g.get("work"))
+        G.ids, G.n_keys, G.slots_per_rank = _p(g.get("ids")), g.get("n_keys", 1), g["slots_per_rank"]
+        G.world, G.n_cols, G.single_row, G.work = g.get("world", 1), len(g["cols"]), int(bool(g.get("single_row"))), _p(g.get("work"))
+        for C, c in zip(G.cols, g["cols"]):
+            p = c["param"]
+            _chk(p, c.get("state0"), c.get("dense"))
+            C.param, C.state0, C.dense_grad = _p(p), _p(c.get("state0")), _p(c.get("dense"))
+            C.width = p.shape[1] if p.dim() > 1 else 1
+            for i, (t, lo, hi, rs) in enumerate(c["src"]):
+                _chk(t)
+                C.src[i], C.lo[i], C.hi[i], C.rank_stride[i] = _p(t), lo, hi, rs
+    return arr
+
+
+def reduce_apply(dtype_of, opt, groups, hyper):
+    """Segment-reduce the contribution rows of every touched row and apply Adagrad in place / write the dense gradient."""
+    _chk(hyper)
+    arr = groups if not isinstance(groups, list) else _red_groups(groups)
+    _lib.check(_lib.lib().chk_reduce_apply(_dt(dtype_of), opt, arr, len(arr), _p(hyper), _stream()), "chk_reduce_apply")
+    _launched(1)
+
+
+def step_finish(dtype_of, works, loss_part, loss_accum, step_id):
+    import ctypes
+    _chk(loss_part, loss_accum, step_id, *works)
+    arr = (ctypes.c_void_p * max(len(works), 1))(*[w.data_ptr() for w in works])
+    _lib.check(_lib.lib().chk_step_finish(_dt(dtype_of), arr, len(works), _p(loss_part), 0 if loss_part is None else loss_part.numel(),
+                                          _p(loss_accum), _p(step_id), _stream()), "chk_step_finish")
+    _launched(1)
+
+
+def dense_apply(opt, tables, hyper, step_id):
+    """tables: list of (param, grad, state0, state1|None) — torch.optim.Adagrad / Adam over whole tables; grads are cleared."""
+    arr = (_lib.DenseTab * len(tables))()
+    for d, (p, g, s0, s1) in zip(arr, tables):
+        _chk(p, g, s0, s1)
+        assert g.numel() == p.numel() and s0.numel() == p.numel()
+        d.param, d.grad, d.state0, d.state1, d.n = _p(p), _p(g), _p(s0), _p(s1), p.numel()
+    _chk(hyper, step_id)
+    _lib.check(_lib.lib().chk_dense_apply(_dt(tables[0][0]), opt, arr, len(tables), _p(hyper), _p(step_id), _stream()), "chk_dense_apply")
+    _launched(1)
+
+
+def rowsum_groups(src, B, nj, width, out):
+    _chk(src, out)
+    _lib.check(_lib.lib().chk_rowsum_groups(_dt(src), _p(src), B, nj, width, _p(out), _stream()), "chk_rowsum_groups")
+    _launched(1)
+
+
+def reg_factors(power, weight, hyper, B, entity, rel, heads, head_stride, rels, tails, tail_stride, g_ent, g_ent_stride, g_rel,
+                g_rel_stride, g_tail, g_tail_stride, loss_part):
+    _chk(hyper, entity, rel, heads, rels, tails, g_ent, g_rel, g_tail, loss_part)
+    _lib.check(_lib.lib().chk_reg_factors(_dt(entity), power, float(weight), _p(hyper), B, _p(entity), entity.shape[1], _p(rel),
+                                          rel.shape[1], _p(heads), head_stride, _p(rels), _p(tails), tail_stride, _p(g_ent),
+                                          g_ent_stride, _p(g_rel), g_rel_stride, _p(g_tail), g_tail_stride, _p(loss_part), _stream()),
+               "chk_reg_factors")
+    _launched(1)

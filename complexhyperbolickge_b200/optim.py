@@ -50,7 +50,10 @@ class KGOptimizer(object):
         self.model, self.regularizer, self.optimizer = model, regularizer, optimizer
         self.optimizer.zero_grad()
         self.batch_size, self.update_steps, self.verbose = batch_size, update_steps, verbose
-        self.double_neg = double_neg            # stored and ignored, exactly like the reference
+        # The reference stores double_neg and ignores it at HEAD; the sampler that used it is still there,
+        # commented out (:78-91): every negative replaces the tail AND, with double_neg, the head.  Restored with those
+        # semantics: negative j of triple b is (h'_bj, r_b, t'_bj), scored with per-pair queries of shape (B, neg, 2).
+        self.double_neg = bool(double_neg)
         self.neg_sample_size = neg_sample_size
         self.n_entities = model.sizes[0]
         self.device = model.entity.weight.device
@@ -60,11 +63,20 @@ class KGOptimizer(object):
                                    device=input_batch.device)
         return torch.where(negsamples < input_batch[:, 2].unsqueeze(-1), negsamples, negsamples + 1)
 
+    def get_neg_heads(self, input_batch):
+        """double_neg: corrupted head per negative, uniform over the entities != true head (mirror of get_neg_samples)."""
+        neg = torch.randint(0, self.n_entities - 1, size=(input_batch.shape[0], self.neg_sample_size), device=input_batch.device)
+        return torch.where(neg < input_batch[:, 0].unsqueeze(-1), neg, neg + 1)
+
     def neg_sampling_loss(self, input_batch):
         positive_score, factors = self.model(input_batch[:, :2].unsqueeze(1), input_batch[:, 2].unsqueeze(1))
         positive_score = F.logsigmoid(positive_score)
         neg_samples = self.get_neg_samples(input_batch)
-        negative_score, _ = self.model(input_batch[:, :2].unsqueeze(1), neg_samples)
+        neg_queries = input_batch[:, :2].unsqueeze(1)
+        if self.double_neg:
+            neg_heads = self.get_neg_heads(input_batch)
+            neg_queries = torch.stack([neg_heads, input_batch[:, 1:2].expand_as(neg_heads)], -1)
+        negative_score, _ = self.model(neg_queries, neg_samples)
         negative_score = F.logsigmoid(-negative_score)
         loss = -torch.cat([positive_score.view(-1), negative_score.view(-1)]).mean()
         return loss, factors

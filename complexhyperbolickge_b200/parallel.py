@@ -135,101 +135,148 @@ class DataParallelKGOptimizer(KGOptimizer):
 
 
 class FusedDataParallelKGOptimizer(FusedKGOptimizer):
-    """Data-parallel version of the fused step (train.FusedKGOptimizer) for ``torch.optim.Adagrad``: every rank runs
-    the fused forward/backward chain on rows ``rank::world`` of the global batch (captured in a CUDA graph), then
+    """Data-parallel version of the fused step (train.FusedKGOptimizer): ``batch_size`` is the GLOBAL batch; every rank runs
+    the fused forward / backward chain on rows ``rank::world`` of it, padded with masked rows to ``ceil(batch_size / world)``
+    so that every step — a ragged last batch and a non-divisible batch included — has the same shapes on every rank and
+    replays ONE CUDA graph that contains the NCCL calls.  The loss terms are normalised by the GLOBAL number of terms, so the
+    sum over ranks of the local gradients is the gradient of the global mean loss.  Gradient reduction, per key group:
 
-    * the touched row ids of every rank are all_gathered (fixed size, no host sync),
-    * each table's gradient is summed over the ranks — a dense all_reduce when the table is smaller than the rows
-      that would have to travel (FB15k-237 / WN18RR-size entity tables, all relation tables), otherwise the sparse
-      (row id, row) exchange of ``exchange_sparse_rows`` (4M-entity table) —
-    * and the row-sparse Adagrad step runs on the union of the touched rows, identically on every rank.
-
-    Local gradients are pre-scaled by 1/world, so the summed gradient is the gradient of the global mean loss."""
+    * **sparse row exchange** (the 4M-entity ``entity`` / ``bh`` / ``bt`` tables): the ranks all_gather their slot ids (small,
+      right after sampling; the grouping of ALL ranks' slots runs beside the local forward / backward) and their flat
+      contribution buffers (gradient rows per slot, duplicates not yet merged); then ONE kernel (chk_reduce_apply) walks
+      the union of the touched rows, sums each row's contributions in (rank, slot) order — the same bits on every replica —
+      and applies the row-sparse Adagrad update in place.  No dense N x 2r gradient exists, nothing is scattered back.
+    * **dense all_reduce** (tables smaller than the rows that would travel: every table at FB15k-237 / WN18RR size, and the
+      relation tables always): the local contributions are segment-reduced into dense gradients that are views of one flat
+      buffer, ONE all_reduce sums it, chk_dense_apply runs torch.optim.Adagrad / Adam over the tables and clears it."""
 
     def __init__(self, *args, process_group=None, sparse_exchange=None, **kw):
-        """sparse_exchange: None = decide per table by size (below); True = the row-sparse tables (entity, bh, bt)
-        always use the sparse row exchange (tests / small-scale checks of the big-table path)."""
+        """sparse_exchange: None = decide by size (below); True / False force the entity-keyed tables onto the sparse row
+        exchange / the dense all_reduce (tests and small-scale checks of the big-table path)."""
         super().__init__(*args, **kw)
         self.pg = process_group
         self.world = _world(process_group)
         self.rank_id = dist.get_rank(process_group) if self.world > 1 else 0
-        self.grad_scale = 1.0 / self.world
-        self.local_batch_size = self.batch_size // self.world      # batch_size is the GLOBAL batch
-        if not (self.fused and self.sparse_adagrad):
-            raise ValueError("FusedDataParallelKGOptimizer needs torch.optim.Adagrad (lr_decay=0, weight_decay=0), a zero "
-                             "regulariser weight and update_steps=1; use DataParallelKGOptimizer otherwise")
-        # Tables whose dense gradient is smaller than the rows that would have to travel are summed with ONE dense
-        # all_reduce: their .grad tensors are views into one flat buffer.  The others use the sparse row exchange.
+        self.stream_id = self.rank_id
+        self.local_batch_size = (self.batch_size + self.world - 1) // self.world
+        self._n_global = self.batch_size
+        if not self.fused or self.kind == "other":
+            raise ValueError("FusedDataParallelKGOptimizer needs torch.optim.Adagrad (lr_decay=0, weight_decay=0) or torch.optim.Adam "
+                             "(defaults), a zero / N3 / F2 regulariser and update_steps=1; use DataParallelKGOptimizer otherwise")
+        m = self.model
+        ent = m.entity.weight
         rows_per_step = self.local_batch_size * (2 + self.neg_sample_size) * self.world
-        params = list(self.model.parameters())
-        forced = set()
-        if sparse_exchange:
-            forced = {id(p) for n, p in self.model.named_parameters() if n.split(".")[0] in SPARSE_TABLES}
-        self._dense = [p for p in params if id(p) not in forced and
-                       p.numel() * p.element_size() <= rows_per_step * ((p.shape[1] if p.dim() > 1 else 1) * p.element_size() + 8)]
-        self._sparse = [p for p in params if not any(p is d for d in self._dense)]
-        if self._dense:
-            flat = torch.zeros(sum(p.numel() for p in self._dense), dtype=params[0].dtype, device=params[0].device)
-            o = 0
-            for p in self._dense:
-                p.grad = flat[o:o + p.numel()].view_as(p)
-                o += p.numel()
-            self._flat_grad = flat
+        travelling = rows_per_step * (ent.shape[1] * ent.element_size() + 8)
+        self.sparse_entity = bool(sparse_exchange) if sparse_exchange is not None else ent.numel() * ent.element_size() > travelling
+        if self.sparse_entity and self.kind != "adagrad":
+            raise ValueError("the sparse row exchange applies row-sparse Adagrad; Adam has dense semantics (every row moves every step)")
+        sparse_names = SPARSE_TABLES if self.sparse_entity else ()
+        self._dense = [p for n, p in m.named_parameters() if n.split(".")[0] not in sparse_names]
+        flat = torch.zeros(sum(p.numel() for p in self._dense), dtype=ent.dtype, device=ent.device)
+        o = 0
+        for p in self._dense:                       # dense gradients are views of ONE flat buffer: one all_reduce sums them all
+            p.grad = flat[o:o + p.numel()].view_as(p)
+            o += p.numel()
+        self._flat_grad = flat
 
-    def _step_body(self, batch):
-        """Local forward/backward, the collectives and the optimizer: every shape is static and nothing synchronises
-        with the host, so the CUDA graph holds the whole step including the NCCL calls."""
-        self._touched = self._forward_backward(batch)
-        self._exchange_and_update()
-
-    def _post_step(self):
-        for p in self.model.parameters():
-            self.optimizer.state[p]["step"] += 1
-
-    def _exchange_and_update(self):
-        m, opt = self.model, self.optimizer
-        heads, rels, tails = self._touched
-        tails = tails.reshape(-1)
-        nb = heads.numel()
-        W = self.world
-        if W > 1:                                    # one all_gather for every touched row id of every rank
-            ids = torch.cat([heads, rels, tails])
-            allids = torch.empty((W, ids.numel()), dtype=ids.dtype, device=ids.device)
-            dist.all_gather_into_tensor(allids, ids, group=self.pg)
-            heads_all, rels_all, tails_all = allids[:, :nb], allids[:, nb:2 * nb], allids[:, 2 * nb:]
-            if self._dense:
-                dist.all_reduce(self._flat_grad, op=dist.ReduceOp.SUM, group=self.pg)
+    # ------------------------------------------------------------------------------------------ plan
+    def _build_groups(self, pl):
+        m = self.model
+        dev = ent_dev = m.entity.weight.device
+        N, R2, W = m.sizes[0], m.rel.weight.shape[0], self.world
+        B, Bq, S_e = pl.B, pl.Bq, pl.S_e
+        pl.w_rel = ops.group_workspace(R2, B, dev)
+        dense_col = lambda p, *src: dict(param=p.data, state0=None, dense=p.grad, src=list(src))
+        if self.sparse_entity:
+            L = pl.flat.numel()
+            pl.all_ids = torch.zeros((W, S_e), dtype=torch.int64, device=ent_dev)
+            pl.all_flat = torch.zeros((W, L), dtype=pl.flat.dtype, device=ent_dev)
+            pl.w_ent = ops.group_workspace(N, W * S_e, dev)
+            pl.ent_group_ids, pl.ent_group_slots = pl.all_ids.view(-1), W * S_e
+            f0, off = pl.all_flat[0], pl.offsets
+            sp_col = lambda p, *src: dict(param=p.data, state0=self._state_of(p), dense=None, src=list(src))
+            ecols = [sp_col(m.entity.weight, (f0[off["g_ent"]:], 0, Bq, L), (f0[off["grow"]:], Bq, S_e, L))]
+            if m.bias == "learn":
+                ecols.append(sp_col(m.bh.weight, (f0[off["gs" if pl.dn else "g_bh"]:], 0, Bq, L)))
+                ecols.append(sp_col(m.bt.weight, (f0[off["gs"]:], Bq, S_e, L)))
+            groups = [dict(ids=pl.ent_group_ids, n_keys=N, slots_per_rank=S_e, world=W, work=pl.w_ent, cols=ecols)]
         else:
-            heads_all, rels_all, tails_all = heads.view(1, -1), rels.view(1, -1), tails.view(1, -1)
-        ent_all = torch.cat([heads_all, tails_all], 1)                   # per rank: [heads | tails], the order of the sent rows
-        zero_row = torch.zeros((1, 1), dtype=torch.int64, device=heads.device)
-        # (table, rows of every rank [W, m_k], this rank's rows)
-        plan = [(m.entity.weight, ent_all, torch.cat([heads, tails])), (m.rel.weight, rels_all, rels),
-                (m.rel_diag.weight, rels_all, rels), (m.c.weight, rels_all if m.multi_c else zero_row, rels if m.multi_c else zero_row.view(-1))]
-        if m._ctx_weight() is not None:
-            plan.append((m._ctx_weight(), rels_all, rels))
-        if m.bias == "learn":
-            plan += [(m.bh.weight, heads_all, heads), (m.bt.weight, tails_all, tails)]
-        if W > 1 and self._sparse:
-            # Big row-sparse tables (the 4M-entity table and its biases): only the touched rows travel.  Send side:
-            # chk_claim_gather_rows (each row once, cleared locally); one all_gather per table; receive side: the
-            # contributions are added back ONE RANK AT A TIME (a launch holds at most one non-zero contribution per
-            # row), so the sum has the same bits on every replica.
-            recv = []
-            for p, rows_all, rows_local in plan:
-                if not any(p is s_ for s_ in self._sparse):
-                    continue
-                sent = ops.claim_gather_rows(p.grad, rows_local.contiguous(), self._stamps[p], self._step_id)
-                got = torch.empty((W,) + tuple(sent.shape), dtype=sent.dtype, device=sent.device)
-                dist.all_gather_into_tensor(got, sent, group=self.pg)
-                recv.append((p, rows_all, got))
-            for k in range(W):
-                ops.multi_scatter_add([dict(grad=p.grad, rows=rows_all[k].contiguous(), src_rows=got[k]) for p, rows_all, got in recv])
-        lr, eps = opt.param_groups[0]["lr"], opt.param_groups[0]["eps"]
-        ops.multi_sparse_adagrad([dict(param=p.data, grad=p.grad, state_sum=opt.state[p]["sum"],
-                                       rows=rows_all.reshape(-1).contiguous(), stamp=self._stamps[p]) for p, rows_all, _ in plan],
-                                 lr, eps, self._step_id)
-        ops.step_counter_bump(self._step_id)
+            pl.w_ent = ops.group_workspace(N, S_e, dev)
+            pl.ent_group_ids, pl.ent_group_slots = pl.ent_ids, S_e
+            ecols = [dense_col(m.entity.weight, (pl.g_ent, 0, Bq, 0), (pl.grow, Bq, S_e, 0))]
+            if m.bias == "learn":
+                ecols.append(dense_col(m.bh.weight, (pl.gs if pl.dn else pl.g_bh, 0, Bq, 0)))
+                ecols.append(dense_col(m.bt.weight, (pl.gs, Bq, S_e, 0)))
+            groups = [dict(ids=pl.ent_ids, n_keys=N, slots_per_rank=S_e, world=1, work=pl.w_ent, cols=ecols)]
+        groups += self._relation_groups(pl, dense_col)
+        pl.groups = groups
+        pl.red = ops._red_groups(groups)
+        pl.works = [pl.w_ent, pl.w_rel]
+
+    def _graph_batch(self):
+        return self.local_batch_size
+
+    def _global_rows(self, n_valid_local):
+        return self._n_global
+
+    # ------------------------------------------------------------------------------------------ step
+    def _after_prep(self, pl):
+        if self.sparse_entity and self.world > 1:           # everyone's slot ids, so the union can be grouped during the local pass
+            dist.all_gather_into_tensor(pl.all_ids.view(-1), pl.ent_ids, group=self.pg)
+        elif self.sparse_entity:
+            pl.all_ids.view(-1).copy_(pl.ent_ids)
+        super()._after_prep(pl)
+
+    def _apply(self, pl):
+        m, st = self.model, self.optimizer.state
+        W = self.world
+        if self.sparse_entity:
+            if W > 1:
+                dist.all_gather_into_tensor(pl.all_flat.view(-1), pl.flat, group=self.pg)
+            else:
+                pl.all_flat.view(-1).copy_(pl.flat)
+        torch.cuda.current_stream().wait_stream(self._side)
+        # one launch: entity-keyed rows of all ranks summed in (rank, slot) order + Adagrad in place (sparse exchange) and / or
+        # the local row sums written into the dense gradients
+        ops.reduce_apply(m.entity.weight, ops.CHK_OPT_ADAGRAD if self.sparse_entity else ops.CHK_OPT_NONE, pl.red, self._hyper)
+        if W > 1:
+            dist.all_reduce(self._flat_grad, op=dist.ReduceOp.SUM, group=self.pg)
+        if self.kind == "adam":
+            tabs = [(p.data, p.grad, st[p]["exp_avg"], st[p]["exp_avg_sq"]) for p in self._dense]
+        else:
+            tabs = [(p.data, p.grad, st[p]["sum"], None) for p in self._dense]
+        ops.dense_apply(ops.CHK_OPT_ADAM if self.kind == "adam" else ops.CHK_OPT_ADAGRAD, tabs, self._hyper, self._step_id)
+        ops.step_finish(m.entity.weight, pl.works, pl.loss_part, self._loss_sum, self._step_id)
 
     def step(self, global_batch):
-        self.fused_step(global_batch[self.rank_id::self.world].to(self.device))
+        """One data-parallel step on a GLOBAL batch (same tensor on every rank, any number of rows <= batch_size)."""
+        n_global = global_batch.shape[0]
+        local = global_batch[self.rank_id::self.world]
+        n_valid = local.shape[0]
+        Bl = self.local_batch_size
+        if n_valid < Bl:                                    # masked padding rows: identical shapes on every rank, every step
+            pad = torch.zeros((Bl, 3), dtype=global_batch.dtype, device=local.device)
+            pad[:n_valid] = local
+            local = pad
+        self._n_global = n_global
+        self.fused_step(local.to(self.device, non_blocking=True), n_valid=n_valid)
+
+    def epoch(self, examples):
+        """KGOptimizer.epoch (reference optimizers/kg_optimizer.py:239-277) data parallel: rank 0's permutation is broadcast,
+        every global batch (the ragged last one too) goes through ``step``; returns the mean over the batches of the GLOBAL
+        mean loss (the same number on every rank)."""
+        n = examples.shape[0]
+        perm = torch.randperm(n).to(self.device)
+        if self.world > 1:
+            dist.broadcast(perm, src=dist.get_global_rank(self.pg, 0) if self.pg is not None else 0, group=self.pg)
+        actual = examples.to(self.device)[perm]
+        self._loss_sum.zero_()
+        nb = 0
+        for b0 in range(0, n, self.batch_size):
+            self.step(actual[b0:b0 + self.batch_size])
+            nb += 1
+        total = self._loss_sum.double().clone()
+        if self.world > 1:
+            dist.all_reduce(total, op=dist.ReduceOp.SUM, group=self.pg)
+        self.sync_optimizer_state()
+        return total.item() / max(nb, 1)

@@ -36,7 +36,7 @@ class EvalState:
         self.entity = ent[self.lo:self.hi].contiguous()
         self.bt = model.bt.weight.detach().view(-1)[self.lo:self.hi].contiguous() if model.bias == "learn" else None
         self.hn = ops.row_hnorm(model.rank, self.entity) if self.hi > self.lo else ent.new_empty(0)
-        self.algo = ops.CHK_RANK_MMA if model.rank_algo == "mma" else ops.CHK_RANK_FMA
+        self.algo = ops.CHK_RANK_MMA if model.resolved_rank_algo() == "mma" else ops.CHK_RANK_FMA
         self.shadow = None
         if self.algo == ops.CHK_RANK_MMA:       # fp32 and fp64 models: bf16x3 prefilter, exact re-check in the model dtype
             self.shadow = ops.entity_shadow(model.rank, self.entity, self.hn, self.bt) if self.hi > self.lo else None
@@ -44,12 +44,14 @@ class EvalState:
 
 def eval_state(model) -> EvalState:
     """The per-pass state is a pure function of the (static during evaluation) entity / bt tables: keep it
-    across get_ranking calls until a parameter is modified in place (torch bumps ``_version``), re-allocated
+    across get_ranking calls until a parameter is modified in place (torch bumps ``_version``; kernels that
+    write through raw pointers bump ``model._param_epoch`` via ``model.parameters_changed()``), re-allocated
     (``data_ptr``) or the tier / sharding changes, so valid/test passes and repeated calls share one shadow."""
     import torch.distributed as dist
     pg = model.process_group
     ent, bt = model.entity.weight, model.bt.weight
-    key = (ent.data_ptr(), ent._version, bt.data_ptr(), bt._version, model.rank_algo, model.bias,
+    key = (ent.data_ptr(), ent._version, bt.data_ptr(), bt._version, getattr(model, "_param_epoch", 0),
+           model.resolved_rank_algo(), model.bias,
            dist.get_world_size(pg) if pg is not None else 1, dist.get_rank(pg) if pg is not None else 0)
     hit = getattr(model, "_eval_cache", None)
     if hit is None or hit[0] != key:

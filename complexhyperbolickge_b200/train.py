@@ -1,22 +1,31 @@
 """Fused negative-sampling training step behind the KGOptimizer contract.
 
 ``FusedKGOptimizer`` has the constructor and the methods of ``KGOptimizer`` (optim.py; reference
-optimizers/kg_optimizer.py:14-316) and produces the same loss and the same parameter update, but ``epoch`` runs
-each batch as ONE chain of our kernels instead of two autograd graphs of eager ops:
+optimizers/kg_optimizer.py:14-316) and produces the same loss and the same parameter update, but ``epoch`` runs each
+batch as ONE short chain of our kernels instead of two autograd graphs of eager ops:
 
-    negatives -> K1 (once: the positive and the negative call share their queries) -> K3 forward on the
-    (B, 1+neg) tails -> chk_nsloss (loss + d/dscores) -> K3 adjoint (tail-row gradients accumulated straight into the
-    dense entity gradient) -> K1 adjoint -> row scatters -> optimizer
+    chk_train_prep (device sampler, id arrays) -> K1 (once: the positive and the negative call share their queries)
+    -> chk_score_gather_train (K3 forward on the (B, 1+neg) tails + loss terms + adjoint, tail rows gathered once)
+    -> K1 adjoint -> chk_reduce_apply (segment-reduce of every touched row's gradient contributions in slot order + the
+    optimizer update of that row) -> chk_step_finish          [chk_group_build runs beside K1/K3 on a second stream]
 
-With ``torch.optim.Adagrad`` (lr_decay = 0, weight_decay = 0) the optimizer step is row-sparse and exact
-(chk_sparse_adagrad on the touched rows of every table, sharing the optimizer's own ``state['sum']`` tensors, so
-``optimizer.state_dict()`` stays valid); any other optimizer gets the dense ``.grad`` and its own ``step()``.  The
-whole chain has static shapes and is captured in a CUDA graph after the first batch (one graph launch per step; a
-ragged last batch replays eagerly).  The loss is accumulated on the device: one host sync per epoch instead of one
-per step (reference :273 ``l.item()``).  The N3 / F2 regularisers (optimizers/regularizers.py:21-58, on the positive
-call's factors entity[h], rel[r], entity[t]) are evaluated in closed form inside the chain: value added to the loss,
-gradient rows 3w|f|f/B (2wf/B) added to the row gradients.  Other regularisers with a non-zero weight and gradient
-accumulation (update_steps > 1) fall back to the unfused contract path of the base class.
+No torch op, no floating-point atomic and no dense N x 2r gradient is on that chain: duplicate rows are segment-reduced in
+a fixed order, so a step is bit-reproducible.  Optimizers:
+
+* ``torch.optim.Adagrad`` (lr_decay = 0, weight_decay = 0): row-sparse and exact, applied in place by chk_reduce_apply on
+  the optimizer's own ``state['sum']`` tensors (a zero-gradient row is a no-op in Adagrad, so sparse == dense);
+* ``torch.optim.Adam`` (no weight decay, no amsgrad): dense semantics (every row moves every step) — the row sums
+  are written into dense gradients and chk_dense_apply updates whole tables with torch's arithmetic on the optimizer's own
+  ``exp_avg`` / ``exp_avg_sq`` tensors;
+* any other optimizer gets the dense ``.grad`` and its own ``step()``.
+
+The chain has static shapes and is captured in a CUDA graph after the first batch (one graph launch per step; a ragged last
+batch runs the same kernels eagerly on its own buffers).  The loss is accumulated on the device: one host sync per epoch
+instead of one per step (reference :273 ``l.item()``).  ``double_neg`` (reference :46, :78-91 — commented out at HEAD) is
+restored with the original's semantics: every negative corrupts the head as well as the tail, so the step runs K1 on
+B(1+neg) per-pair queries.  N3 / F2 (optimizers/regularizers.py:21-58, on the positive call's factors) are evaluated by
+chk_reg_factors inside the chain.  Other regularisers with a non-zero weight and gradient accumulation (update_steps > 1)
+fall back to the unfused contract path of the base class.
 """
 import torch
 
@@ -24,8 +33,59 @@ from . import ops
 from .optim import KGOptimizer
 
 
+def _round4(n: int) -> int:
+    return (n + 3) // 4 * 4
+
+
+class _Plan:
+    """Static buffers and reduce descriptors of the step for one local batch size."""
+
+    def __init__(self, o: "FusedKGOptimizer", B: int):
+        m = o.model
+        dev, dt = m.entity.weight.device, m.entity.weight.dtype
+        r, n = m.rank, m.dim
+        self.B, self.nt = B, o.neg_sample_size + 1
+        nt = self.nt
+        self.dn = bool(o.double_neg)
+        self.Bq = Bq = B * nt if self.dn else B           # queries of the step
+        self.P = P = B * nt                               # (query, tail) pairs
+        i64 = dict(dtype=torch.int64, device=dev)
+        self.batch = torch.zeros((B, 3), **i64)
+        self.ent_ids = torch.zeros((Bq + P,), **i64)      # slot -> entity id: [heads | tails], the entity group's key array
+        self.heads, self.tails = self.ent_ids[:Bq], self.ent_ids[Bq:]
+        self.rels = torch.zeros((Bq,), **i64)
+        self.rels_b = self.rels if not self.dn else torch.zeros((B,), **i64)
+        att = m._ctx_weight() is not None
+        wrd = m.rel_diag.weight.shape[1]
+        # contributions of the entity group live in ONE flat buffer (it is what travels in the data-parallel exchange)
+        o_ent, o_row, o_gs = 0, _round4(Bq * 2 * r), 0
+        o_gs = o_row + _round4(P * 2 * r)
+        o_bh = o_gs + _round4(P)
+        flat_len = o_bh + (0 if self.dn else _round4(B))
+        self.flat = torch.zeros((flat_len,), dtype=dt, device=dev)
+        self.g_ent = self.flat[o_ent:o_ent + Bq * 2 * r].view(Bq, 2 * r)
+        self.grow = self.flat[o_row:o_row + P * 2 * r].view(P, 2 * r)
+        self.gs = self.flat[o_gs:o_gs + P].view(B, nt)
+        self.g_bh = None if self.dn else self.flat[o_bh:o_bh + B]
+        mk = lambda *s: torch.zeros(s, dtype=dt, device=dev)
+        self.q, self.c_out, self.grad_q = mk(Bq, 2 * r), mk(Bq), mk(Bq, 2 * r)
+        self.g_rel, self.g_rd, self.g_c = mk(Bq, 2 * n), mk(Bq, wrd), mk(Bq)
+        self.g_ctx = mk(Bq, n) if att else None
+        if self.dn:                                       # per-pair relation-row gradients are summed over j first
+            self.s_rel, self.s_rd, self.s_c = mk(B, 2 * n), mk(B, wrd), mk(B)
+            self.s_ctx = mk(B, n) if att else None
+        else:
+            self.s_rel, self.s_rd, self.s_c, self.s_ctx = self.g_rel, self.g_rd, self.g_c, self.g_ctx
+        self.loss_part = mk(B)
+        self.inj_t = self.inj_h = None
+        self.S_e = Bq + P                                 # entity-group slots per rank
+        self.graph = None
+        self.offsets = dict(g_ent=o_ent, grow=o_row, gs=o_gs, g_bh=o_bh)      # element offsets inside ``flat``
+        o._build_groups(self)
+
+
 class FusedKGOptimizer(KGOptimizer):
-    def __init__(self, *args, use_cuda_graph: bool = True, **kw):
+    def __init__(self, *args, use_cuda_graph: bool = True, seed=None, **kw):
         super().__init__(*args, **kw)
         m = self.model
         w = getattr(self.regularizer, "weight", None)
@@ -35,123 +95,216 @@ class FusedKGOptimizer(KGOptimizer):
             self._reg = (3 if kind == "N3" else 2, float(w))
         self.fused = (w == 0 or w == 0.0 or self._reg is not None) and self.update_steps == 1 and m.entity.weight.is_cuda
         opt = self.optimizer
-        self.sparse_adagrad = (type(opt) is torch.optim.Adagrad and
-                               all(g["lr_decay"] == 0 and g["weight_decay"] == 0 and not g.get("maximize", False)
-                                   for g in opt.param_groups))
+        if len(opt.param_groups) != 1:               # one set of hyper-parameters is baked into the device scalars
+            self.fused = False
+        g0 = opt.param_groups[0]
+        if type(opt) is torch.optim.Adagrad and g0["lr_decay"] == 0 and g0["weight_decay"] == 0 and not g0.get("maximize", False) \
+                and g0.get("initial_accumulator_value", 0) == 0:
+            self.kind = "adagrad"
+        elif type(opt) is torch.optim.Adam and g0["weight_decay"] == 0 and not g0["amsgrad"] and not g0.get("maximize", False) \
+                and not g0.get("capturable", False) and not g0.get("fused", False):
+            self.kind = "adam"
+        else:
+            self.kind = "other"
+        self.sparse_adagrad = self.kind == "adagrad"
         self.use_cuda_graph = use_cuda_graph
-        self._graph = None
-        self._static_batch = None
-        dev = m.entity.weight.device
-        self._loss_sum = torch.zeros((), dtype=m.entity.weight.dtype, device=dev)
-        self._step_id = torch.ones((), dtype=torch.int32, device=dev)
-        self._stamps = {}
-        self.local_batch_size = self.batch_size      # data parallel: batch_size / world
-        self.grad_scale = 1.0                        # data parallel: 1/world (mean over ranks of the local mean losses)
-        if self.fused:
-            for p in m.parameters():                 # static dense gradient buffers, all-zero between steps
+        self.seed = int(torch.initial_seed() if seed is None else seed)
+        self.stream_id = 0                           # data parallel: the rank (distinct negative streams per rank)
+        self.world = 1
+        self._plans = {}
+        self._steps_done = 0
+        if not self.fused:
+            return
+        dev, dt = m.entity.weight.device, m.entity.weight.dtype
+        self._loss_sum = torch.zeros((), dtype=dt, device=dev)
+        self._hyper = torch.zeros(ops.CHK_HYPER_LEN, dtype=torch.float64, device=dev)
+        self._hyper_key = None
+        self._side = torch.cuda.Stream(device=dev)
+        start = 0
+        if self.kind == "adam":
+            for p in m.parameters():                 # torch.optim.Adam creates its state lazily: create it the way it would
+                st = opt.state[p]
+                if len(st) == 0:
+                    st["step"] = torch.tensor(0.0, dtype=torch.float32)
+                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                start = max(start, int(st["step"].item()))
+        elif self.kind == "adagrad":
+            start = max(int(opt.state[p]["step"].item()) for p in m.parameters())
+        self._steps_done = start
+        self._step_id = torch.full((), start + 1, dtype=torch.int32, device=dev)      # 1-based number of the NEXT step
+        if self.kind != "adagrad":
+            for p in m.parameters():                 # dense gradients, all-zero between steps
                 if p.grad is None:
                     p.grad = torch.zeros_like(p)
-            if self.sparse_adagrad:
-                for p in m.parameters():
-                    self._stamps[p] = torch.zeros(p.shape[0], dtype=torch.int32, device=dev)
+
+    # ------------------------------------------------------------------------------------------ pieces
+    def _state_of(self, p):
+        return self.optimizer.state[p]["sum"]
+
+    def _injected_sampler(self):
+        return type(self).get_neg_samples is not KGOptimizer.get_neg_samples
+
+    def _global_rows(self, B_local_valid: int) -> int:
+        return B_local_valid                          # data parallel: the valid rows of ALL ranks
+
+    def _set_hyper(self, n_valid_local: int, n_rows_global: int):
+        g = self.optimizer.param_groups[0]
+        b1, b2 = g.get("betas", (0.0, 0.0))
+        eps = g.get("eps", 0.0)
+        key = (g["lr"], eps, n_valid_local, n_rows_global, b1, b2)
+        if key == self._hyper_key:
+            return
+        h = torch.tensor([g["lr"], eps, 1.0 / (n_rows_global * (self.neg_sample_size + 1)), float(n_valid_local), b1, b2,
+                          1.0 / n_rows_global, 0.0], dtype=torch.float64)
+        self._hyper.copy_(h)                          # stream-ordered after the earlier steps, which read the old values
+        self._hyper_key = key
+
+    def _build_groups(self, pl: _Plan):
+        """Grouping workspaces + reduce descriptors (single process: every slot is local)."""
+        m = self.model
+        dev = m.entity.weight.device
+        N, R2 = m.sizes[0], m.rel.weight.shape[0]
+        B, Bq, S_e = pl.B, pl.Bq, pl.S_e
+        pl.w_ent = ops.group_workspace(N, S_e, dev)
+        pl.w_rel = ops.group_workspace(R2, B, dev)
+        pl.ent_group_ids, pl.ent_group_slots = pl.ent_ids, S_e
+        inplace = self.kind == "adagrad"
+
+        def col(p, *src):
+            return dict(param=p.data, state0=self._state_of(p) if inplace else None, dense=None if inplace else p.grad, src=list(src))
+        ecols = [col(m.entity.weight, (pl.g_ent, 0, Bq, 0), (pl.grow, Bq, S_e, 0))]
+        if m.bias == "learn":
+            ecols.append(col(m.bh.weight, (pl.gs if pl.dn else pl.g_bh, 0, Bq, 0)))
+            ecols.append(col(m.bt.weight, (pl.gs, Bq, S_e, 0)))
+        groups = [dict(ids=pl.ent_ids, n_keys=N, slots_per_rank=S_e, world=1, work=pl.w_ent, cols=ecols)]
+        groups += self._relation_groups(pl, col)
+        pl.groups = groups
+        pl.red = ops._red_groups(groups)
+        pl.works = [pl.w_ent, pl.w_rel]
+
+    def _relation_groups(self, pl: _Plan, col):
+        """Relation-keyed tables (rel, rel_diag, context_vec, c): B slots, one per triple."""
+        m = self.model
+        B, R2 = pl.B, m.rel.weight.shape[0]
+        rcols = [col(m.rel.weight, (pl.s_rel, 0, B, 0)), col(m.rel_diag.weight, (pl.s_rd, 0, B, 0))]
+        if pl.s_ctx is not None:
+            rcols.append(col(m._ctx_weight(), (pl.s_ctx, 0, B, 0)))
+        if m.multi_c:
+            rcols.append(col(m.c.weight, (pl.s_c, 0, B, 0)))
+            return [dict(ids=pl.rels_b, n_keys=R2, slots_per_rank=B, world=1, work=pl.w_rel, cols=rcols)]
+        return [dict(ids=pl.rels_b, n_keys=R2, slots_per_rank=B, world=1, work=pl.w_rel, cols=rcols),
+                dict(ids=None, slots_per_rank=B, world=1, work=None, single_row=True, cols=[col(m.c.weight, (pl.s_c, 0, B, 0))])]
+
+    def _plan(self, B):
+        pl = self._plans.get(B)
+        if pl is None:
+            pl = self._plans[B] = _Plan(self, B)
+        return pl
 
     # ------------------------------------------------------------------------------------------ one fused step
-    def _forward_backward(self, batch):
+    def _forward_backward(self, pl: _Plan):
+        """prep -> K1 -> K3 training pass -> K1 adjoint [-> row sums over j, regulariser]; grouping on the side stream."""
         m = self.model
         r = m.rank
-        ent, rel, rd, cw = m.entity.weight, m.rel.weight, m.rel_diag.weight, m.c.weight
+        ent, rel, rd, cw = m.entity.weight.data, m.rel.weight.data, m.rel_diag.weight.data, m.c.weight.data
         ctx = m._ctx_weight()
-        heads, rels = batch[:, 0].contiguous(), batch[:, 1].contiguous()
-        negs = self.get_neg_samples(batch)
-        tails = torch.cat([batch[:, 2:3], negs], 1).contiguous()
-        B, nt = tails.shape
+        ctx = None if ctx is None else ctx.data
+        B, nt, Bq = pl.B, pl.nt, pl.Bq
         learn = m.bias == "learn"
-        with torch.no_grad():
-            q, _ = ops.query_fwd(m.KIND, r, bool(m.multi_c), ent, rel, rd, ctx, cw, heads, rels)
-            bh_vals = m.bh.weight.view(-1)[heads].contiguous() if learn else None
-            scores = ops.score_gather_fwd(r, B, nt, q, 1, 0, ent, tails, 0, bh_vals, 1 if learn else 0, 0,
-                                          m.bt.weight.view(-1) if learn else None)
-            gs = ops.nsloss(scores, self._loss_sum)
-            if self.grad_scale != 1.0:
-                gs.mul_(self.grad_scale)
-            grad_q = ops.score_gather_bwd_scatter(r, B, nt, q, 1, 0, ent, tails, gs, ent.grad)
-            g_ent, g_rel, g_rd, g_ctx, g_c = ops.query_bwd(m.KIND, r, bool(m.multi_c), ent, rel, rd, ctx, cw, heads, rels, grad_q)
-            tabs = [dict(grad=ent.grad, rows=heads, src_rows=g_ent), dict(grad=rel.grad, rows=rels, src_rows=g_rel),
-                    dict(grad=rd.grad, rows=rels, src_rows=g_rd)]
-            if self._reg is not None:                # reg = w * sum_f sum |f|^p / B over (entity[h], rel[r], entity[t])
-                power, w = self._reg
-                pos = batch[:, 2].contiguous()
-                fh, fr, ft = ent[heads], rel[rels], ent[pos]
-                if power == 3:
-                    val = (fh.abs() ** 3).sum() + (fr.abs() ** 3).sum() + (ft.abs() ** 3).sum()
-                    dh, dr, dt = 3 * fh.abs() * fh, 3 * fr.abs() * fr, 3 * ft.abs() * ft
-                else:
-                    val = (fh ** 2).sum() + (fr ** 2).sum() + (ft ** 2).sum()
-                    dh, dr, dt = 2 * fh, 2 * fr, 2 * ft
-                self._loss_sum += val * (w / B)
-                k = w / B * self.grad_scale
-                g_ent.add_(dh, alpha=k)
-                g_rel.add_(dr, alpha=k)
-                tabs.append(dict(grad=ent.grad, rows=pos, src_rows=(dt * k).contiguous()))
-            if ctx is not None:
-                tabs.append(dict(grad=ctx.grad, rows=rels, src_rows=g_ctx))
-            if m.multi_c:
-                tabs.append(dict(grad=cw.grad, rows=rels, src_rows=g_c))
-            else:
-                cw.grad += g_c.sum()
-            if learn:
-                tabs.append(dict(grad=m.bh.weight.grad, rows=heads, src_rows=gs.sum(1).contiguous()))
-                tabs.append(dict(grad=m.bt.weight.grad, rows=tails.view(-1), src_rows=gs))
-            ops.multi_scatter_add(tabs)          # all row scatters of the step in one launch
-        return heads, rels, tails
+        inj_t = inj_h = None
+        if self._injected_sampler():                  # an overridden get_neg_samples is honoured (tests inject negatives)
+            inj_t = self.get_neg_samples(pl.batch).contiguous()
+            if pl.dn:
+                inj_h = self.get_neg_heads(pl.batch).contiguous()
+        ops.train_prep(pl.batch, self.neg_sample_size, self.n_entities, pl.dn, self.seed, self._step_id, self.stream_id,
+                       pl.heads, pl.rels, pl.tails, inj_t, inj_h)
+        if pl.dn:
+            pl.rels_b.copy_(pl.batch[:, 1])
+        self._after_prep(pl)
+        ops.query_fwd(m.KIND, r, bool(m.multi_c), ent, rel, rd, ctx, cw, pl.heads, pl.rels, out=(pl.q, pl.c_out))
+        qsb, qsj = (nt, 1) if pl.dn else (1, 0)
+        ops.score_gather_train(r, B, nt, pl.q, qsb, qsj, ent, pl.tails, pl.heads if learn else None, qsb, qsj,
+                               m.bh.weight.data.view(-1) if learn else None, m.bt.weight.data.view(-1) if learn else None,
+                               self._hyper, pl.loss_part, pl.gs, pl.grad_q, pl.grow, pl.g_bh if learn else None)
+        ops.query_bwd_into(m.KIND, r, bool(m.multi_c), ent, rel, rd, ctx, cw, pl.heads, pl.rels, pl.grad_q, pl.g_ent, pl.g_rel,
+                           pl.g_rd, pl.g_ctx, pl.g_c)
+        if pl.dn:
+            ops.rowsum_groups(pl.g_rel, B, nt, pl.g_rel.shape[1], pl.s_rel)
+            ops.rowsum_groups(pl.g_rd, B, nt, pl.g_rd.shape[1], pl.s_rd)
+            ops.rowsum_groups(pl.g_c, B, nt, 1, pl.s_c)
+            if pl.g_ctx is not None:
+                ops.rowsum_groups(pl.g_ctx, B, nt, pl.g_ctx.shape[1], pl.s_ctx)
+        if self._reg is not None:
+            power, w = self._reg
+            hs = nt if pl.dn else 1
+            ops.reg_factors(power, w, self._hyper, B, ent, rel, pl.heads, hs, pl.rels, pl.tails, nt, pl.g_ent, hs * 2 * r,
+                            pl.s_rel, pl.s_rel.shape[1], pl.grow, nt * 2 * r, pl.loss_part)
 
-    def _sparse_step(self, heads, rels, tails):
-        m, opt = self.model, self.optimizer
-        lr, eps = opt.param_groups[0]["lr"], opt.param_groups[0]["eps"]
-        ent_rows = torch.cat([heads, tails.view(-1)])
-        zero_row = torch.zeros(1, dtype=torch.int64, device=heads.device)
-        plan = [(m.entity.weight, ent_rows), (m.rel.weight, rels), (m.rel_diag.weight, rels),
-                (m.c.weight, rels if m.multi_c else zero_row)]
-        if m._ctx_weight() is not None:
-            plan.append((m._ctx_weight(), rels))
-        if m.bias == "learn":
-            plan += [(m.bh.weight, heads), (m.bt.weight, tails.view(-1))]
-        ops.multi_sparse_adagrad([dict(param=p.data, grad=p.grad, state_sum=opt.state[p]["sum"], rows=rows.contiguous(),
-                                       stamp=self._stamps[p]) for p, rows in plan], lr, eps, self._step_id)
-        ops.step_counter_bump(self._step_id)
+    def _after_prep(self, pl):
+        """Ids are known: group the slots by row beside the forward / backward kernels (second stream)."""
+        cur = torch.cuda.current_stream()
+        self._side.wait_stream(cur)
+        with torch.cuda.stream(self._side):
+            ops.group_build(pl.ent_group_ids, self.model.sizes[0], pl.w_ent)
+            ops.group_build(pl.rels_b, self.model.rel.weight.shape[0], pl.w_rel)
 
-    def _step_body(self, batch):
-        heads, rels, tails = self._forward_backward(batch)
-        if self.sparse_adagrad:
-            self._sparse_step(heads, rels, tails)
+    def _apply(self, pl):
+        """Segment-reduce + optimizer."""
+        m = self.model
+        torch.cuda.current_stream().wait_stream(self._side)
+        ops.reduce_apply(m.entity.weight, ops.CHK_OPT_ADAGRAD if self.kind == "adagrad" else ops.CHK_OPT_NONE, pl.red, self._hyper)
+        if self.kind == "adam":
+            st = self.optimizer.state
+            ops.dense_apply(ops.CHK_OPT_ADAM, [(p.data, p.grad, st[p]["exp_avg"], st[p]["exp_avg_sq"]) for p in m.parameters()],
+                            self._hyper, self._step_id)
+        ops.step_finish(m.entity.weight, pl.works, pl.loss_part, self._loss_sum, self._step_id)
 
-    def fused_step(self, batch):
-        """One training step on a device batch (B, 3); the loss is added to the device-side epoch accumulator."""
-        full = batch.shape[0] == self.local_batch_size
-        if self.use_cuda_graph and full:
-            if self._graph is None:
-                self._static_batch = batch.clone()
-                self._step_body(self._static_batch)           # warm-up (allocator, lazy init) — a real step
+    def _step_body(self, pl):
+        self._forward_backward(pl)
+        self._apply(pl)
+
+    def fused_step(self, batch, n_valid=None):
+        """One training step on a device batch (B, 3); the loss is added to the device-side epoch accumulator.  n_valid < B
+        marks the trailing rows as padding (zero loss, zero gradient)."""
+        B = batch.shape[0]
+        if B == 0:
+            return
+        n_valid = B if n_valid is None else n_valid
+        self._set_hyper(n_valid, self._global_rows(n_valid))
+        pl = self._plan(B)
+        graph_ok = self.use_cuda_graph and self.kind != "other" and B == self._graph_batch()
+        pl.batch.copy_(batch, non_blocking=True)
+        if graph_ok:
+            if pl.graph is None:
+                self._step_body(pl)                               # warm-up (lazy init, allocator) — a real step
                 self._post_step()
                 torch.cuda.synchronize()
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
-                    self._step_body(self._static_batch)
-                self._graph = g
-                return                                        # the capture pass does not execute: this batch was the warm-up step
-            self._static_batch.copy_(batch)
-            self._graph.replay()
+                    self._step_body(pl)
+                pl.graph = g
+                return                                            # the capture pass does not execute: this batch was the warm-up step
+            pl.graph.replay()
         else:
-            self._step_body(batch)
+            self._step_body(pl)
         self._post_step()
 
+    def _graph_batch(self):
+        return self.batch_size
+
     def _post_step(self):
-        if self.sparse_adagrad:
-            for p in self.model.parameters():                 # keep torch's bookkeeping in sync (unused when lr_decay = 0)
-                self.optimizer.state[p]["step"] += 1
-        else:
+        self._steps_done += 1
+        self.model.parameters_changed()                           # cached evaluation state (norms, shadow) is stale now
+        if self.kind == "other":
             self.optimizer.step()
             self.optimizer.zero_grad(set_to_none=False)
+
+    def sync_optimizer_state(self):
+        """torch's per-parameter step counters (bookkeeping only) follow the fused steps; called once per epoch."""
+        if self.kind in ("adagrad", "adam"):
+            for p in self.model.parameters():
+                self.optimizer.state[p]["step"].fill_(float(self._steps_done))
 
     # ------------------------------------------------------------------------------------------ contract
     def epoch(self, examples):
@@ -163,4 +316,5 @@ class FusedKGOptimizer(KGOptimizer):
         for b0 in range(0, examples.shape[0], self.batch_size):
             self.fused_step(actual[b0:b0 + self.batch_size])
             n += 1
+        self.sync_optimizer_state()
         return self._loss_sum.item() / max(n, 1)

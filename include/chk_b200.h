@@ -137,6 +137,80 @@ int chk_multi_scatter_add(int dtype, const chk_table_desc* tabs, int n_tables, v
 int chk_multi_sparse_adagrad(int dtype, const chk_table_desc* tabs, int n_tables, double lr, double eps,
                              const int32_t* step_id, void* stream);
 
+/* ---- fused training step: sampler, fused loss, segment-reduce + optimizer -------------------
+ * One optimisation step of KGOptimizer.epoch (optimizers/kg_optimizer.py:239-277) = chk_train_prep -> chk_query_fwd ->
+ * chk_score_gather_train -> chk_query_bwd -> [chk_group_build beside them] -> chk_reduce_apply -> chk_step_finish, with no
+ * host synchronisation, no floating-point atomics (bit-reproducible) and no dense N x 2r gradient.
+ *
+ * Device scalars shared by the step kernels, `hyper` (double[CHK_HYPER_LEN], written by the host between steps):
+ *   [0] lr  [1] eps  [2] 1/(loss terms of the GLOBAL batch = rows*(1+neg))  [3] valid rows of this rank's batch (rows beyond
+ *   it are padding: zero loss, zero gradient)  [4] beta1  [5] beta2  [6] 1/(rows of the global batch)  [7] reserved. */
+#define CHK_HYPER_LEN 8
+enum { CHK_OPT_NONE = 0, CHK_OPT_ADAGRAD = 1, CHK_OPT_ADAM = 2 };
+
+/* KGOptimizer.get_neg_samples (optimizers/kg_optimizer.py:92-99) on the device: tails[b,0] = batch[b,2], tails[b,j>=1] uniform
+ * over the entities != batch[b,2] (Philox4x32-10 keyed by `seed`, counter = (b*neg+j-1, *step_id, stream_id)), or copied from
+ * injected_tails [B,neg] when given (an overridden sampler).  double_neg = 0: heads [B], rels [B] are columns 0, 1 of the batch.
+ * double_neg = 1 (semantics of the commented-out original, :78-91: every negative also corrupts the head): heads, rels are
+ * [B,1+neg]; heads[b,0] = batch[b,0], heads[b,j>=1] uniform over the entities != batch[b,0] (or injected_heads), rels[b,:] = r. */
+int chk_train_prep(const int64_t* batch, int64_t B, int64_t neg, int64_t n_entities, int double_neg,
+                   const int64_t* injected_tails, const int64_t* injected_heads, uint64_t seed,
+                   const int32_t* step_id, uint32_t stream_id, int64_t* heads, int64_t* rels, int64_t* tails, void* stream);
+
+/* K3 training pass: scores of the (B, nt) gathered tails, the loss terms of KGOptimizer.neg_sampling_loss (:115-122; column 0
+ * positive: -logsigmoid(s), others -logsigmoid(-s), scaled by hyper[2]) and the adjoint, tail rows gathered once.
+ * Out: loss_part [B] (row sums of the scaled terms), grad_scores [B,nt] (= the bt gradient of every pair), grad_q (strides of q;
+ * reduced over j when q_stride_j == 0), grad_rows [B*nt,2r], g_bh [B] (sum_j grad_scores; NULL with per-pair queries).
+ * bias: bh value of pair (b,j) = bh[head_idx[b*head_stride_b + j*head_stride_j]]; bh/bt both NULL for bias 'none'. */
+int chk_score_gather_train(int dtype, int rank, int64_t B, int64_t nt,
+                           const void* q, int64_t q_stride_b, int64_t q_stride_j,
+                           const void* table, const int64_t* tail_idx,
+                           const int64_t* head_idx, int64_t head_stride_b, int64_t head_stride_j,
+                           const void* bh, const void* bt, const double* hyper,
+                           void* loss_part, void* grad_scores, void* grad_q, void* grad_rows, void* g_bh, void* stream);
+
+/* Grouping of `total_slots` slots by the table row they name (ids[s] in [0, n_keys)): fills the workspace (int32, size
+ * chk_group_workspace_bytes, zero-initialised once by the caller; chk_reduce_apply / chk_step_finish leave it ready for
+ * the next step) with per-row counts, segment bases, the slot order and the list of touched rows. */
+int64_t chk_group_workspace_bytes(int64_t n_keys, int64_t total_slots);
+int chk_group_build(const int64_t* ids, int64_t total_slots, int64_t n_keys, void* work, void* stream);
+
+/* Segment-reduce + apply.  A group = one key space (entity ids; relation ids) with world*slots_per_rank slots numbered
+ * rank-major (slot = k*slots_per_rank + s); a column = one table fed by up to two contribution sources: local slot s in
+ * [lo[i], hi[i]) of rank k contributes the row src[i] + k*rank_stride[i] + (s-lo[i])*width (elements).  Every touched row's
+ * contributions are summed in ascending slot order by one warp, then either the torch.optim.Adagrad update (lr_decay = 0,
+ * weight_decay = 0: sum += g*g; p -= lr*g/(sqrt(sum)+eps), hyper[0..1]) is applied to the row in place (dense_grad NULL,
+ * opt = CHK_OPT_ADAGRAD, state0 = the optimizer's `sum`), or the row sum is WRITTEN to dense_grad[row] (other rows untouched).
+ * single_row: every slot names row 0 (the (1,1) curvature table), no grouping workspace.  width must be 1 or even. */
+#define CHK_RED_MAX_COLS 4
+#define CHK_RED_MAX_GROUPS 3
+typedef struct chk_red_col {
+    void* param; void* state0; void* dense_grad; int64_t width;
+    const void* src[2]; int64_t lo[2], hi[2], rank_stride[2];
+} chk_red_col;
+typedef struct chk_red_group {
+    const int64_t* ids; int64_t n_keys; int64_t slots_per_rank; int32_t world; int32_t n_cols; int32_t single_row; int32_t pad_;
+    void* work; chk_red_col cols[CHK_RED_MAX_COLS];
+} chk_red_group;
+int chk_reduce_apply(int dtype, int opt, const chk_red_group* groups, int n_groups, const double* hyper, void* stream);
+/* End of a step: resets the grouping headers, adds the per-row loss partials (fixed order) to *loss_accum, bumps *step_id.
+ * loss_part / step_id may be NULL. */
+int chk_step_finish(int dtype, void* const* group_works, int n_groups, const void* loss_part, int64_t n_loss, void* loss_accum,
+                    int32_t* step_id, void* stream);
+/* torch.optim.Adagrad / torch.optim.Adam (defaults: no weight decay, no amsgrad; hyper[0,1,4,5], *step_id = 1-based step) over
+ * whole tables from a dense gradient, which is cleared (run.py:205 hands the dense tables to torch.optim). */
+typedef struct chk_dense_tab { void* param; void* grad; void* state0; void* state1; int64_t n; } chk_dense_tab;
+int chk_dense_apply(int dtype, int opt, const chk_dense_tab* tabs, int n_tables, const double* hyper, const int32_t* step_id, void* stream);
+/* out[b,:] = sum_j in[b,j,:] in ascending j (double_neg: the nt per-pair relation-row gradients of a triple share a row). */
+int chk_rowsum_groups(int dtype, const void* in, int64_t B, int64_t nj, int64_t width, void* out, void* stream);
+/* N3 (power 3) / F2 (power 2) of the positive call's factors entity[h], rel[r], entity[t] (optimizers/regularizers.py:21-58):
+ * value weight*sum|f|^p*hyper[6] added to loss_part[b], gradient rows added to the three contribution rows of triple b. */
+int chk_reg_factors(int dtype, int power, double weight, const double* hyper, int64_t B,
+                    const void* entity, int64_t ent_width, const void* rel, int64_t rel_width,
+                    const int64_t* heads, int64_t head_stride, const int64_t* rels, const int64_t* tails, int64_t tail_stride,
+                    void* g_ent_rows, int64_t g_ent_stride, void* g_rel_rows, int64_t g_rel_stride,
+                    void* g_tail_rows, int64_t g_tail_stride, void* loss_part, void* stream);
+
 /* ---- K2: scoring against the whole entity table + filtered rank counts (evaluation) -------------
  * All K2 entry points share ONE canonical pair-score arithmetic (ascending-k FMA chain, see
  * csrc/chk_common.cuh) so that target scores, tile counts, the filter pass and the exact re-check of the

@@ -1,11 +1,17 @@
-"""GPU: the fused training step (train.FusedKGOptimizer: K1 + K3 + chk_nsloss + adjoints + row-sparse Adagrad, CUDA
-graph) against the unfused KGOptimizer contract path (two model() calls + autograd + dense torch.optim) on identical
-batches and injected negatives: same losses, same parameters after several steps."""
+"""GPU: the fused training step (train.FusedKGOptimizer: chk_train_prep + K1 + chk_score_gather_train + K1 adjoint +
+chk_group_build + chk_reduce_apply [+ chk_dense_apply], CUDA graph) against
+  * the reference's own loss curves (tests/golden/curve_*: batches and negatives replayed, Adagrad and Adam),
+  * the unfused KGOptimizer contract path (two model() calls + autograd + dense torch.optim) on identical batches and injected
+    negatives (all three models, fp32 / fp64, N3 / F2, double_neg, duplicate rows),
+and the step kernels one by one (sampler contract, segment-reduce vs index_add, dense Adam vs torch.optim.Adam, bit
+reproducibility, the data-parallel receive side emulated with two ranks' buffers on one GPU)."""
 from argparse import Namespace
 
 import numpy as np
 import pytest
 import torch
+
+from conftest import golden_files, load_case
 
 pytestmark = pytest.mark.gpu
 
@@ -23,31 +29,44 @@ def _mk(name, rank, dtype, n_ent=700, n_rel2=10, seed=0, bias="learn", multi_c=T
 def _feed(cls):
     class Fed(cls):
         def get_neg_samples(self, input_batch):
-            return self._negs_static
+            return self._negs_static[:input_batch.shape[0]]
+
+        def get_neg_heads(self, input_batch):
+            return self._negh_static[:input_batch.shape[0]]
     return Fed
 
 
+CASES = [("FFTRotH", 33, "double", None, False, True), ("FFTRefH", 33, "float", None, False, True),
+         ("FFTAttH", 17, "double", None, False, True), ("FFTRotH", 257, "float", None, False, True),
+         ("FFTRefH", 33, "double", ("N3", 0.05), False, True), ("FFTAttH", 33, "double", ("F2", 0.01), False, True),
+         ("FFTRotH", 33, "float", ("N3", 0.05), False, True),
+         ("FFTRotH", 33, "double", None, True, True), ("FFTAttH", 17, "double", ("N3", 0.05), True, True),
+         ("FFTRefH", 9, "float", None, True, False), ("FFTRotH", 65, "double", None, False, False),
+         ("FFTRotH", 257, "double", None, False, True)]
+
+
 @pytest.mark.parametrize("graph", [False, True])
-@pytest.mark.parametrize("opt_name", ["Adagrad", "Adam"])
-@pytest.mark.parametrize("name,rank,dtype,reg", [("FFTRotH", 33, "double", None), ("FFTRefH", 33, "float", None),
-                                                ("FFTAttH", 17, "double", None), ("FFTRotH", 257, "float", None),
-                                                ("FFTRefH", 33, "double", ("N3", 0.05)), ("FFTAttH", 33, "double", ("F2", 0.01)),
-                                                ("FFTRotH", 33, "float", ("N3", 0.05))])
-def test_fused_step_matches_contract_path(name, rank, dtype, reg, opt_name, graph):
+@pytest.mark.parametrize("opt_name", ["Adagrad", "Adam", "SGD"])
+@pytest.mark.parametrize("name,rank,dtype,reg,double_neg,multi_c", CASES)
+def test_fused_step_matches_contract_path(name, rank, dtype, reg, double_neg, multi_c, opt_name, graph):
     from complexhyperbolickge_b200 import optim
     from complexhyperbolickge_b200.optim import KGOptimizer
-    N3 = (lambda _w: getattr(optim, reg[0])(reg[1])) if reg else optim.N3      # regulariser under test (weight 0 by default)
     from complexhyperbolickge_b200.train import FusedKGOptimizer
+    if opt_name == "SGD" and (graph or reg or rank > 33):
+        pytest.skip("generic-optimizer fallback: covered on the small cases, eager only")
+    mkreg = (lambda: getattr(optim, reg[0])(reg[1])) if reg else (lambda: optim.N3(0.0))
     B, neg, steps, n_ent, n_rel2 = 48, 21, 5, 700, 10
-    a, b = _mk(name, rank, dtype), _mk(name, rank, dtype)
+    a, b = _mk(name, rank, dtype, multi_c=multi_c), _mk(name, rank, dtype, multi_c=multi_c)
     b.load_state_dict(a.state_dict())
-    mk_opt = (lambda ps: torch.optim.Adagrad(ps, lr=0.05)) if opt_name == "Adagrad" else (lambda ps: torch.optim.Adam(ps, lr=1e-3))
-    ref = _feed(KGOptimizer)(a, N3(0.0), mk_opt(a.parameters()), B, 1, neg, False, verbose=False)
-    fus = _feed(FusedKGOptimizer)(b, N3(0.0), mk_opt(b.parameters()), B, 1, neg, False, verbose=False, use_cuda_graph=graph)
-    assert fus.fused and fus.sparse_adagrad == (opt_name == "Adagrad")
+    mk_opt = {"Adagrad": lambda ps: torch.optim.Adagrad(ps, lr=0.05), "Adam": lambda ps: torch.optim.Adam(ps, lr=1e-3),
+              "SGD": lambda ps: torch.optim.SGD(ps, lr=0.05, momentum=0.5)}[opt_name]
+    ref = _feed(KGOptimizer)(a, mkreg(), mk_opt(a.parameters()), B, 1, neg, double_neg, verbose=False)
+    fus = _feed(FusedKGOptimizer)(b, mkreg(), mk_opt(b.parameters()), B, 1, neg, double_neg, verbose=False, use_cuda_graph=graph)
+    assert fus.fused and fus.kind == {"Adagrad": "adagrad", "Adam": "adam", "SGD": "other"}[opt_name]
     g = torch.Generator().manual_seed(5)
-    ref._negs_static = torch.zeros(B, neg, dtype=torch.int64, device="cuda")
-    fus._negs_static = torch.zeros(B, neg, dtype=torch.int64, device="cuda")
+    for o in (ref, fus):
+        o._negs_static = torch.zeros(B, neg, dtype=torch.int64, device="cuda")
+        o._negh_static = torch.zeros(B, neg, dtype=torch.int64, device="cuda")
     losses_ref = []
     fus._loss_sum.zero_()
     for i in range(steps):
@@ -56,8 +75,12 @@ def test_fused_step_matches_contract_path(name, rank, dtype, reg, opt_name, grap
         if i == 2:
             batch[:7] = batch[7:14]                    # duplicate triples / rows inside a batch
         negs = torch.randint(0, n_ent, (B, neg), generator=g).cuda()
-        ref._negs_static.copy_(negs)
-        fus._negs_static.copy_(negs)
+        negh = torch.randint(0, n_ent, (B, neg), generator=g).cuda()
+        if i == 3:
+            negs[:, :5] = negs[0, 0]                   # one row named by many slots (a long segment)
+        for o in (ref, fus):
+            o._negs_static.copy_(negs)
+            o._negh_static.copy_(negh)
         l = ref.calculate_loss(batch)
         l.backward()
         ref.optimizer.step()
@@ -70,16 +93,216 @@ def test_fused_step_matches_contract_path(name, rank, dtype, reg, opt_name, grap
     for (k, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
         scale = max(pa.abs().max().item(), 1e-30)
         err = (pa - pb).abs().max().item() / scale
-        assert err <= (1e-8 if dbl else 5e-3), (k, err)
-        assert pb.grad is None or pb.grad.abs().max().item() == 0 or not fus.sparse_adagrad, k   # grads cleared row-wise
-    if opt_name == "Adagrad":                            # optimizer state is the torch optimizer's own, kept in sync
+        # fp32: Adagrad's first steps move a coordinate by ~lr * sign(g), so coordinates whose gradient is rounding noise
+        # differ between two summation orders; the bound is loose in fp32 and the fp64 runs (1e-8) carry the parity claim
+        assert err <= (1e-8 if dbl else (5e-3 if rank <= 65 else 3e-2)), (k, err)
+    fus.sync_optimizer_state()
+    if opt_name in ("Adagrad", "Adam"):                  # optimizer state is the torch optimizer's own, kept in sync
+        keys = ("sum",) if opt_name == "Adagrad" else ("exp_avg", "exp_avg_sq")
         for pa, pb in zip(a.parameters(), b.parameters()):
-            sa, sb = ref.optimizer.state[pa]["sum"], fus.optimizer.state[pb]["sum"]
-            assert (sa - sb).abs().max().item() <= (1e-12 if dbl else 1e-4) * max(sa.abs().max().item(), 1e-30)
+            for key in keys:
+                sa, sb = ref.optimizer.state[pa][key], fus.optimizer.state[pb][key]
+                assert (sa - sb).abs().max().item() <= (1e-9 if dbl else 1e-3) * max(sa.abs().max().item(), 1e-30), key
+            assert float(fus.optimizer.state[pb]["step"]) == float(ref.optimizer.state[pa]["step"]) == steps
+
+
+@pytest.mark.parametrize("path", golden_files("curve_"), ids=lambda p: p.split("/")[-1][6:-4])
+@pytest.mark.parametrize("graph", [False, True])
+def test_fused_optimizer_vs_reference_curve(path, graph):
+    """The fused optimizer replays the REFERENCE's own 3-epoch run (tests/golden/curve_*: the reference's batches, negatives,
+    per-step losses and final parameters; Adagrad and Adam): losses to 1e-9, parameters to 1e-8."""
+    from test_gpu_parity import _close, _model_from_case
+    from complexhyperbolickge_b200.optim import N3
+    from complexhyperbolickge_b200.train import FusedKGOptimizer
+    case = load_case(path)
+    model = _model_from_case(case, "p0_")
+    optim_name, lr = case["regime"], float(case["lr"])
+    neg = case["neg_cat"].shape[1]
+    opt = _feed(FusedKGOptimizer)(model, N3(0.0), getattr(torch.optim, optim_name)(model.parameters(), lr=lr), batch_size=64,
+                                  update_steps=1, neg_sample_size=neg, double_neg=False, verbose=False, use_cuda_graph=graph)
+    assert opt.fused and opt.kind == optim_name.lower()
+    opt._negs_static = torch.zeros(64, neg, dtype=torch.int64, device="cuda")
+    off, losses, prev = 0, [], 0.0
+    opt._loss_sum.zero_()
+    for L in case["batch_lens"]:
+        L = int(L)
+        opt._negs_static[:L].copy_(torch.from_numpy(case["neg_cat"][off:off + L]))
+        opt.fused_step(torch.from_numpy(case["batch_cat"][off:off + L]).cuda())
+        off += L
+        cur = opt._loss_sum.item()
+        losses.append(cur - prev)
+        prev = cur
+    err = np.abs(np.array(losses) - case["step_losses"]).max()
+    assert err <= 1e-9, err
+    for k, p in model.named_parameters():
+        _close(p, case["pT_" + k.replace(".weight", "")], 1e-8, "final " + k)
+
+
+@pytest.mark.parametrize("double_neg", [False, True])
+def test_fused_step_bit_reproducible(double_neg):
+    """Two runs from the same state with the device sampler (same seed): identical bits in every parameter (fp32; no
+    floating-point atomics, duplicates segment-reduced in slot order), graph replay included."""
+    from complexhyperbolickge_b200.optim import N3
+    from complexhyperbolickge_b200.train import FusedKGOptimizer
+    g = torch.Generator().manual_seed(1)
+    ex = torch.stack([torch.randint(0, 300, (640,), generator=g) % 40, torch.randint(0, 10, (640,), generator=g),
+                      torch.randint(0, 300, (640,), generator=g)], 1).cuda()          # few distinct heads: many duplicates
+    finals = []
+    for _ in range(2):
+        m = _mk("FFTRotH", 33, "float", n_ent=300)
+        opt = FusedKGOptimizer(m, N3(0.0), torch.optim.Adagrad(m.parameters(), lr=0.05), 64, 1, 30, double_neg, verbose=False, seed=77)
+        for i in range(10):
+            opt.fused_step(ex[i * 64:(i + 1) * 64])
+        finals.append([p.detach().clone() for p in m.parameters()] + [opt._loss_sum.clone()])
+    for x, y in zip(*finals):
+        assert torch.equal(x, y)
+    assert np.isfinite(finals[0][-1].item())
+
+
+def test_device_sampler_contract():
+    """chk_train_prep == get_neg_samples' contract (reference optimizers/kg_optimizer.py:92-99): ids in range, never the true
+    tail (head), uniform; a new stream per step and per rank; injected negatives are passed through."""
+    from complexhyperbolickge_b200 import ops
+    B, neg, N = 256, 50, 37
+    g = torch.Generator().manual_seed(0)
+    batch = torch.stack([torch.randint(0, N, (B,), generator=g), torch.randint(0, 5, (B,), generator=g),
+                         torch.randint(0, N, (B,), generator=g)], 1).cuda()
+    step = torch.ones((), dtype=torch.int32, device="cuda")
+    out = {}
+    for dn in (False, True):
+        nq = B * (neg + 1) if dn else B
+        heads, rels = torch.zeros(nq, dtype=torch.int64, device="cuda"), torch.zeros(nq, dtype=torch.int64, device="cuda")
+        tails = torch.zeros(B, neg + 1, dtype=torch.int64, device="cuda")
+        ops.train_prep(batch, neg, N, dn, 1234, step, 0, heads, rels, tails)
+        assert torch.equal(tails[:, 0], batch[:, 2])
+        t = tails[:, 1:]
+        assert t.min() >= 0 and t.max() < N and not (t == batch[:, 2:3]).any()
+        hist = torch.bincount(t.reshape(-1), minlength=N).float()
+        assert hist.min() > 0.7 * B * neg / N and hist.max() < 1.3 * B * neg / N
+        if dn:
+            h = heads.view(B, neg + 1)
+            assert torch.equal(h[:, 0], batch[:, 0]) and torch.equal(rels.view(B, neg + 1), batch[:, 1:2].expand(B, neg + 1))
+            assert h.min() >= 0 and h.max() < N and not (h[:, 1:] == batch[:, 0:1]).any()
+            assert not torch.equal(h[:, 1:], t)
+        else:
+            assert torch.equal(heads, batch[:, 0]) and torch.equal(rels, batch[:, 1])
+        out[dn] = tails.clone()
+        again = torch.zeros_like(tails)
+        ops.train_prep(batch, neg, N, dn, 1234, step, 0, heads, rels, again)
+        assert torch.equal(again, tails)                                   # counter-based: same (seed, step, rank) -> same ids
+        ops.train_prep(batch, neg, N, dn, 1234, step, 1, heads, rels, again)
+        assert not torch.equal(again, tails)                               # another rank draws another stream
+        inj = torch.randint(0, N, (B, neg), generator=g).cuda()
+        ops.train_prep(batch, neg, N, dn, 1234, step, 0, heads, rels, again, injected_tails=inj, injected_heads=inj if dn else None)
+        assert torch.equal(again[:, 1:], inj)
+    step2 = torch.full((), 2, dtype=torch.int32, device="cuda")
+    heads, rels = torch.zeros(B, dtype=torch.int64, device="cuda"), torch.zeros(B, dtype=torch.int64, device="cuda")
+    nxt = torch.zeros(B, neg + 1, dtype=torch.int64, device="cuda")
+    ops.train_prep(batch, neg, N, False, 1234, step2, 0, heads, rels, nxt)
+    assert not torch.equal(nxt, out[False])
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("world", [1, 2])
+@pytest.mark.parametrize("mode", ["adagrad", "dense"])
+def test_reduce_apply_matches_index_add(dtype, world, mode):
+    """chk_group_build + chk_reduce_apply against index_add_ + the Adagrad formula: two sources per column (heads | tails
+    layout), a scalar column, segments of every size class (1, <= 32, <= 2048, > 2048 slots), `world` ranks' buffers
+    (rank-major slot numbering with a rank stride — the receive side of the data-parallel exchange)."""
+    from complexhyperbolickge_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    N, w, Bq, P = 500, 66, 40, 3000
+    S = Bq + P
+    ids = torch.randint(0, N, (world, S), generator=g)
+    ids[:, Bq + 100:Bq + 100 + 2500] = 7                 # a > 2048-slot segment
+    ids[:, Bq + 2600:Bq + 2600 + 300] = 11               # a shared-memory-sort segment
+    flat_len = Bq * w + P * w + P + 8
+    flat = torch.randn(world, flat_len, generator=g, dtype=torch.float64).to(dtype)
+    a_rows, b_rows = flat[:, :Bq * w].view(world, Bq, w), flat[:, Bq * w:Bq * w + P * w].view(world, P, w)
+    sc = flat[:, Bq * w + P * w:Bq * w + P * w + P]
+    want = torch.zeros(N, w, dtype=torch.float64)
+    want_s = torch.zeros(N, dtype=torch.float64)
+    for k in range(world):
+        want.index_add_(0, ids[k, :Bq], a_rows[k].double())
+        want.index_add_(0, ids[k, Bq:], b_rows[k].double())
+        want_s.index_add_(0, ids[k, Bq:], sc[k].double())
+    ids_d, flat_d = ids.cuda().contiguous(), flat.cuda().contiguous()
+    param = torch.randn(N, w, generator=g, dtype=torch.float64).to(dtype).cuda()
+    pscal = torch.randn(N, 1, generator=g, dtype=torch.float64).to(dtype).cuda()
+    p0, ps0 = param.clone(), pscal.clone()
+    ssum, ssum_s = torch.rand(N, w, generator=g, dtype=torch.float64).to(dtype).cuda(), torch.rand(N, 1, generator=g, dtype=torch.float64).to(dtype).cuda()
+    s0, ss0 = ssum.clone(), ssum_s.clone()
+    dense, dense_s = torch.full((N, w), 9.0, dtype=dtype, device="cuda"), torch.full((N, 1), 9.0, dtype=dtype, device="cuda")
+    work = ops.group_workspace(N, world * S, "cuda")
+    hyper = torch.tensor([0.1, 1e-10, 0, 0, 0, 0, 0, 0], dtype=torch.float64, device="cuda")
+    f0 = flat_d[0]
+    inplace = mode == "adagrad"
+    cols = [dict(param=param, state0=ssum if inplace else None, dense=None if inplace else dense,
+                 src=[(f0, 0, Bq, flat_len), (f0[Bq * w:], Bq, S, flat_len)]),
+            dict(param=pscal, state0=ssum_s if inplace else None, dense=None if inplace else dense_s,
+                 src=[(f0[Bq * w + P * w:], Bq, S, flat_len)])]
+    groups = [dict(ids=ids_d.view(-1), n_keys=N, slots_per_rank=S, world=world, work=work, cols=cols)]
+    results = []
+    for rep in range(2):
+        param.copy_(p0); pscal.copy_(ps0); ssum.copy_(s0); ssum_s.copy_(ss0)
+        ops.group_build(ids_d.view(-1), N, work)
+        ops.reduce_apply(param, ops.CHK_OPT_ADAGRAD if inplace else ops.CHK_OPT_NONE, groups, hyper)
+        ops.step_finish(param, [work], None, None, None)
+        assert work[:4].abs().sum().item() == 0 and work[4:4 + N].abs().sum().item() == 0     # counts / headers ready for the next step
+        results.append((param.clone(), pscal.clone(), dense.clone(), dense_s.clone()))
+    for x, y in zip(*results):
+        assert torch.equal(x, y)                            # bit-reproducible whatever order the atomics grouped the slots in
+    tol = 1e-12 if dtype == torch.float64 else 2e-5
+    touched = torch.zeros(N, dtype=torch.bool)
+    touched[ids.view(-1)] = True
+    if inplace:
+        gsum = want.cuda()
+        acc = s0.double() + gsum * gsum
+        exp = p0.double() - 0.1 * gsum / (acc.sqrt() + 1e-10)
+        assert (param.double() - exp).abs().max().item() <= tol * 50
+        assert (ssum.double() - acc).abs().max().item() <= tol * acc.abs().max().item()
+        gs_ = want_s.cuda().unsqueeze(1)
+        acc_s = ss0.double() + gs_ * gs_
+        assert (pscal.double() - (ps0.double() - 0.1 * gs_ / (acc_s.sqrt() + 1e-10))).abs().max().item() <= tol * 50
+        assert torch.equal(param[~touched.cuda()], p0[~touched.cuda()])
+    else:
+        assert (dense.double().cpu()[touched] - want[touched]).abs().max().item() <= tol * want.abs().max().item()
+        assert (dense_s.double().cpu()[touched, 0] - want_s[touched]).abs().max().item() <= tol * want_s.abs().max().item()
+        assert (dense[~touched.cuda()] == 9.0).all()        # untouched rows are not written
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("opt_name", ["Adam", "Adagrad"])
+def test_dense_apply_matches_torch(dtype, opt_name):
+    """chk_dense_apply == torch.optim.Adam / Adagrad step by step (row-sparse gradients, state carried over 6 steps)."""
+    from complexhyperbolickge_b200 import ops
+    g = torch.Generator().manual_seed(2)
+    p_ref = torch.nn.Parameter(torch.randn(300, 10, generator=g, dtype=torch.float64).to(dtype).cuda())
+    p = p_ref.detach().clone()
+    opt = torch.optim.Adam([p_ref], lr=3e-3) if opt_name == "Adam" else torch.optim.Adagrad([p_ref], lr=0.05)
+    s0, s1 = torch.zeros_like(p), torch.zeros_like(p)
+    step = torch.ones((), dtype=torch.int32, device="cuda")
+    hyper = torch.tensor([3e-3 if opt_name == "Adam" else 0.05, 1e-8 if opt_name == "Adam" else 1e-10, 0, 0, 0.9, 0.999, 0, 0],
+                         dtype=torch.float64, device="cuda")
+    for t in range(6):
+        grad = torch.zeros(300, 10, dtype=dtype)
+        rows = torch.randint(0, 300, (40,), generator=g)
+        grad[rows] = torch.randn(40, 10, generator=g, dtype=torch.float64).to(dtype)
+        p_ref.grad = grad.cuda()
+        opt.step()
+        gd = grad.cuda().clone()
+        ops.dense_apply(ops.CHK_OPT_ADAM if opt_name == "Adam" else ops.CHK_OPT_ADAGRAD, [(p, gd, s0, s1 if opt_name == "Adam" else None)],
+                        hyper, step)
+        ops.step_finish(p, [], None, None, step)
+        assert gd.abs().max().item() == 0                  # the dense gradient is cleared
+    tol = 1e-13 if dtype == torch.float64 else 3e-6
+    assert (p - p_ref.detach()).abs().max().item() <= tol * p_ref.abs().max().item()
+    key = "exp_avg" if opt_name == "Adam" else "sum"
+    assert (s0 - opt.state[p_ref][key]).abs().max().item() <= tol * max(opt.state[p_ref][key].abs().max().item(), 1e-30)
+    assert int(step.item()) == 7
 
 
 def test_fused_epoch_runs_and_learns():
-    from complexhyperbolickge_b200 import synthetic
     from complexhyperbolickge_b200.optim import N3
     from complexhyperbolickge_b200.train import FusedKGOptimizer
     m = _mk("FFTRotH", 33, "float", n_ent=2000, n_rel2=8)
@@ -96,12 +319,76 @@ def test_fused_epoch_runs_and_learns():
     assert not opt2.fused and np.isfinite(opt2.epoch(ex[:300]))
     opt3 = FusedKGOptimizer(m, N3(0.01), torch.optim.Adagrad(m.parameters(), lr=0.1), 100, 1, 50, False, verbose=False)
     assert opt3.fused and np.isfinite(opt3.epoch(ex[:300]))
+    # reduce_lr (reference optimizers/kg_optimizer.py:56-67) reaches the captured graph through the device scalars
+    before = m.entity.weight.detach().clone()
+    for gq in opt3.optimizer.param_groups:
+        gq["lr"] = 0.0
+    opt3.epoch(ex[:300])
+    assert torch.equal(before, m.entity.weight.detach())
+
+
+def test_train_eval_train_eval_sees_new_parameters():
+    """the fused step writes parameters through raw pointers; the cached evaluation state (Hermitian norms,
+    bf16 shadow) must be rebuilt after it — ranks after training equal a fresh model loaded with the trained weights."""
+    import complexhyperbolickge_b200 as chk
+    from complexhyperbolickge_b200.optim import N3
+    from complexhyperbolickge_b200.train import FusedKGOptimizer
+    for algo in ("fma", "mma"):
+        m = _mk("FFTRotH", 33, "float", n_ent=1500, n_rel2=8)
+        m.rank_algo = algo
+        opt = FusedKGOptimizer(m, N3(0.0), torch.optim.Adagrad(m.parameters(), lr=0.5), 100, 1, 50, False, verbose=False)
+        g = torch.Generator().manual_seed(0)
+        ex = torch.stack([torch.randint(0, 1500, (400,), generator=g), torch.randint(0, 8, (400,), generator=g),
+                          torch.randint(0, 1500, (400,), generator=g)], 1)
+        filters = {}
+        for h, r, t in ex.tolist():
+            filters.setdefault((h, r), []).append(t)
+        r0 = m.get_ranking(ex[:200], filters, batch_size=64)
+        opt.epoch(ex)
+        r1 = m.get_ranking(ex[:200], filters, batch_size=64)
+        opt.epoch(ex)
+        r2 = m.get_ranking(ex[:200], filters, batch_size=64)
+        fresh = _mk("FFTRotH", 33, "float", n_ent=1500, n_rel2=8)
+        fresh.rank_algo = algo
+        fresh.load_state_dict(m.state_dict())
+        assert torch.equal(r2, fresh.get_ranking(ex[:200], filters, batch_size=64))
+        assert not torch.equal(r0, r1) and r2.mean() < r0.mean()
+
+
+@pytest.mark.parametrize("sparse", [True, False])
+@pytest.mark.parametrize("opt_name", ["Adagrad", "Adam"])
+def test_fused_dp_single_rank_paths_equal_fused(sparse, opt_name):
+    """FusedDataParallelKGOptimizer with one rank (no process group) runs the sparse-exchange path (gathered buffers + in-place
+    Adagrad) or the dense path (segment-reduce into the flat gradient + chk_dense_apply): both must reproduce the single-GPU
+    fused step BIT for bit — same slot order, same arithmetic.  A ragged last batch goes through the padded fixed-shape step."""
+    from complexhyperbolickge_b200.optim import N3
+    from complexhyperbolickge_b200.parallel import FusedDataParallelKGOptimizer
+    from complexhyperbolickge_b200.train import FusedKGOptimizer
+    if sparse and opt_name == "Adam":
+        pytest.skip("the sparse row exchange is Adagrad only")
+    g = torch.Generator().manual_seed(4)
+    ex = torch.stack([torch.randint(0, 400, (230,), generator=g), torch.randint(0, 10, (230,), generator=g),
+                      torch.randint(0, 400, (230,), generator=g)], 1)
+    mk_opt = (lambda ps: torch.optim.Adagrad(ps, lr=0.05)) if opt_name == "Adagrad" else (lambda ps: torch.optim.Adam(ps, lr=1e-3))
+    outs = []
+    for cls, kw in ((FusedKGOptimizer, {}), (FusedDataParallelKGOptimizer, dict(sparse_exchange=sparse))):
+        m = _mk("FFTRefH", 33, "double", n_ent=400)
+        opt = cls(m, N3(0.0), mk_opt(m.parameters()), 64, 1, 20, False, verbose=False, seed=5, **kw)
+        torch.manual_seed(11)
+        losses = [opt.epoch(ex), opt.epoch(ex)]
+        outs.append((losses, [p.detach().clone() for p in m.parameters()]))
+    assert np.allclose(outs[0][0], outs[1][0], rtol=0, atol=1e-12)
+    for x, y in zip(outs[0][1], outs[1][1]):
+        if opt_name == "Adagrad":
+            assert torch.equal(x, y)
+        else:
+            assert (x - y).abs().max().item() <= 1e-12 * x.abs().max().item()
 
 
 @pytest.mark.parametrize("dtype,width", [(torch.float32, 66), (torch.float64, 130), (torch.float32, 1)])
 def test_claim_gather_rows_sends_each_row_once(dtype, width):
-    """Send side of the data-parallel sparse exchange (chk_claim_gather_rows): duplicates of a row carry zeros, the
-    claimed rows are cleared in the dense gradient, untouched rows are left alone; claims last for one step."""
+    """chk_claim_gather_rows (C ABI, round-1 send side of the sparse exchange; the fused optimizers now exchange per-slot
+    contribution rows instead): duplicates of a row carry zeros, the claimed rows are cleared in the dense gradient."""
     from complexhyperbolickge_b200 import ops
     g = torch.Generator().manual_seed(0)
     N = 50
