@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--no-train", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the BASELINE configs[0..3] legs and the K1/K3 kernel rooflines")
     return ap.parse_args()
 
 
@@ -124,8 +125,8 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------ watchdog
 class Watchdog:
     """Per-phase deadlines.  A phase that exceeds its deadline (a hung collective, a rank that lost its GPU, a box that
-    pages for minutes) must not hang the job: every rank dumps its Python stacks to stderr and exits 0; rank 0 first
-    prints the JSON line with whatever has been measured so far plus an "error" key naming the phase."""
+    pages for minutes) must not hang the job: every rank dumps its Python stacks to stderr and exits with code 3; rank 0
+    first prints the JSON line with whatever has been measured so far plus an "error" key naming the phase."""
 
     def __init__(self, rank_id):
         self.rank_id, self.phase, self.deadline, self.partial = rank_id, "start", None, None
@@ -157,7 +158,7 @@ class Watchdog:
                     line = dict(self.partial) if self.partial else {"metric": METRIC, "value": None, "unit": UNIT}
                     line["error"] = f"phase '{self.phase}' exceeded its deadline and was abandoned"
                     self.emit(line)
-                os._exit(0)
+                os._exit(3)                       # the partial line is printed, but a hung phase is a failure
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
@@ -250,220 +251,42 @@ def oracle_train_sample(steps=10):
             "sample": f"{steps} steps of B={B}, neg={neg} (forward + analytic backward, no optimizer), {sum(ts):.1f} s of CPU work"}
 
 
-# ------------------------------------------------------------------------------------------------ train leg
-def dp_train_leg(steps, warmup, device, pg, world):
-    """Data-parallel training (parallel.DataParallelKGOptimizer): configs[1] shape, 500 triples per rank per step
-    (weak scaling), sparse row-gradient all_gather + dense all_reduce of the relation tables over NCCL."""
-    from argparse import Namespace
-    import torch.distributed as dist
-    import complexhyperbolickge_b200 as chk
-    from complexhyperbolickge_b200 import synthetic
-    from complexhyperbolickge_b200.optim import N3
-    from complexhyperbolickge_b200.parallel import FusedDataParallelKGOptimizer
-    g = synthetic.make_graph("fb237", seed=0)
-    args = Namespace(sizes=(g["n_ent"], g["n_rel2"], g["n_ent"]), rank=33, dropout=0, gamma=0, dtype="float",
-                     bias="learn", init_size=1e-3, multi_c=True)
-    model = chk.FFTRefH(args).to(device)
-    synthetic.trained_like_(model, 0)
-    B = 500 * world
-    opt = FusedDataParallelKGOptimizer(model, N3(0.0), torch.optim.Adagrad(model.parameters(), lr=0.02), B, 1, 250, False,
-                                       verbose=False, process_group=pg)
-    steps *= 10
-    ex = synthetic.train_examples(g)
-    ex = ex[torch.randperm(ex.shape[0], generator=torch.Generator().manual_seed(0))][: (steps + warmup) * B].to(device)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    loss = None
-    for i in range(steps + warmup):
-        if i == warmup:
-            torch.cuda.synchronize()
-            dist.barrier()
-            ev0.record()
-        opt.step(ex[i * B:(i + 1) * B])
-    lv = opt._loss_sum.item() / (steps + warmup)
-    ev1.record()
-    torch.cuda.synchronize()
-    t = torch.tensor([ev0.elapsed_time(ev1) / steps], device=device)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = t.item()
-    return {"metric": "train_triples_per_sec", "value": B / (ms * 1e-3), "unit": "triples/s", "ms_per_step": ms,
-            "scaling": "weak", "global_batch": B,
-            "config": f"BASELINE.json configs[1] shape: FFTRefH rank=33 Adagrad neg=250, 500 triples per rank x{world}, "
-                      "fused step per rank (CUDA graph) + all_gather of touched row ids + dense all_reduce of the (small) table gradients "
-                      "[sparse row exchange for tables larger than the touched rows] + row-sparse Adagrad on the union",
-            "mean_loss_rank0": lv}
+# ------------------------------------------------------------------------------------------------ shared helpers
+def load_peaks():
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    return json.load(open(pk)) if os.path.exists(pk) else {}
 
 
-def train_big_leg(model, graph, steps, warmup, device, pg, world):
-    """Training on BASELINE.json configs[4] (the 4M-entity graph, FFTRotH rank 257): fused step per rank on 500 triples
-    (neg = 100), row-sparse Adagrad on the 8.2 GB table.  N > 1: data parallel with replicated tables (weak scaling, 500
-    triples per rank); the touched gradient rows travel (chk_claim_gather_rows + all_gather + rank-ordered scatter),
-    never the dense 8.2 GB gradient."""
-    import torch.distributed as dist
-    from complexhyperbolickge_b200 import synthetic
-    from complexhyperbolickge_b200.optim import N3
-    from complexhyperbolickge_b200.parallel import FusedDataParallelKGOptimizer
-    from complexhyperbolickge_b200.train import FusedKGOptimizer
-    neg, B = 100, 500 * world
-    model.train()
-    adagrad = torch.optim.Adagrad(model.parameters(), lr=0.02)
-    if world > 1:
-        # beyond 2 ranks the step runs eagerly: it is exchange-bound (hundreds of MB of gradient rows per step), so the
-        # ~50 launches cost nothing, and no multi-hundred-MB NCCL collective has to be captured into a CUDA graph
-        opt = FusedDataParallelKGOptimizer(model, N3(0.0), adagrad, B, 1, neg, False, verbose=False, process_group=pg,
-                                           use_cuda_graph=world <= 2)
-    else:
-        opt = FusedKGOptimizer(model, N3(0.0), adagrad, B, 1, neg, False, verbose=False)
-    ex = synthetic.train_examples(graph)
-    ex = ex[torch.randperm(ex.shape[0], generator=torch.Generator().manual_seed(0))[: (steps + warmup) * B]]
-    pinned = ex.pin_memory()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    for i in range(steps + warmup):
-        if i == warmup:
-            torch.cuda.synchronize()
-            if world > 1:
-                dist.barrier()
-            opt._loss_sum.zero_()
-            ev0.record()
-        b = pinned[i * B:(i + 1) * B].to(device, non_blocking=True)      # H2D of the step's batch inside the timed region
-        if world > 1:
-            opt.step(b)
-        else:
-            opt.fused_step(b)
-    lv = opt._loss_sum.item() / steps
-    ev1.record()
-    torch.cuda.synchronize()
-    ms = ev0.elapsed_time(ev1) / steps
-    if world > 1:
-        t = torch.tensor([ms], device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = t.item()
-    rank = model.rank
-    bytes_per_triple = 2 * (2 + neg) * 2 * rank * 4
-    out = {"metric": "train_triples_per_sec", "value": B / (ms * 1e-3), "unit": "triples/s", "ms_per_step": ms,
-           "scaling": "weak", "global_batch": B, "mean_loss_rank0": lv,
-           "config": f"BASELINE.json configs[4]: FFTRotH rank={rank} Adagrad, 500 triples per rank x{world}, neg={neg}, synthetic 4M-entity "
-                     "graph; fused step (K1 + K3 + loss + adjoints + row-sparse Adagrad" + (", CUDA graph" if world <= 2 else ", eager launches")
-                     + "), batch H2D from pinned memory each step"
-                     + ("; replicated tables, sparse gradient-row exchange (claim-gather + all_gather + rank-ordered scatter)"
-                        if world > 1 else ""),
-           "algorithmic_bytes_per_triple": bytes_per_triple,
-           "hbm_frac_per_gpu": B / world / (ms * 1e-3) * bytes_per_triple / 1e9 / 6530.0}
-    if world > 1:
-        m = 500 * (2 + neg)
-        out["exchange_bytes_per_rank_per_step"] = world * m * (2 * rank * 4 + 2 * 4 + 8)
-    del opt, adagrad
-    for p in model.parameters():
-        p.grad = None
-    return out
-
-
-def train_leg(steps, warmup, device):
-    """Training throughput on BASELINE.json configs[1]: FFTRefH rank=33 Adagrad bs=500 neg=250 on the synthetic
-    FB15k-237 shape.  Two numbers: the fused step (train.FusedKGOptimizer: one kernel chain + row-sparse Adagrad in a
-    CUDA graph; same loss and update) and the unfused drop-in KGOptimizer contract loop (two model() calls, autograd,
-    dense torch.optim).  Each step's batch comes from pinned host memory (H2D inside the timed region)."""
+def make_model(model_name, rank, dtype, graph, device, multi_c=True):
     from argparse import Namespace
     import complexhyperbolickge_b200 as chk
     from complexhyperbolickge_b200 import synthetic
-    from complexhyperbolickge_b200.optim import KGOptimizer, N3
-    from complexhyperbolickge_b200.train import FusedKGOptimizer
-    g = synthetic.make_graph("fb237", seed=0)
-    args = Namespace(sizes=(g["n_ent"], g["n_rel2"], g["n_ent"]), rank=33, dropout=0, gamma=0, dtype="float",
-                     bias="learn", init_size=1e-3, multi_c=True)
-    ex = synthetic.train_examples(g)
-    ex = ex[torch.randperm(ex.shape[0], generator=torch.Generator().manual_seed(0))]
-    out = {}
-    for mode, n_steps in (("fused", 10 * steps), ("drop_in", steps)):
-        model = chk.FFTRefH(args).to(device)
-        synthetic.trained_like_(model, 0)
-        cls = FusedKGOptimizer if mode == "fused" else KGOptimizer
-        opt = cls(model, N3(0.0), torch.optim.Adagrad(model.parameters(), lr=0.02), 500, 1, 250, False, verbose=False)
-        pinned = ex[: (n_steps + warmup) * 500].pin_memory()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        loss = None
-        for i in range(n_steps + warmup):
-            if i == warmup:
-                torch.cuda.synchronize()
-                if mode == "fused":
-                    opt._loss_sum.zero_()
-                ev0.record()
-            b = pinned[i * 500:(i + 1) * 500].to(device, non_blocking=True)
-            if mode == "fused":
-                opt.fused_step(b)
-            else:
-                loss = opt.calculate_loss(b)
-                loss.backward()
-                opt.optimizer.step()
-                opt.optimizer.zero_grad()
-        lv = opt._loss_sum.item() / n_steps if mode == "fused" else loss.item()
-        ev1.record()
-        torch.cuda.synchronize()
-        ms = ev0.elapsed_time(ev1) / n_steps
-        out[mode] = {"value": 500.0 / (ms * 1e-3), "ms_per_step": ms, "loss": lv}
-    bytes_per_triple = 2 * (2 + 250) * 66 * 4
-    return {"metric": "train_triples_per_sec", "value": out["fused"]["value"], "unit": "triples/s",
-            "ms_per_step": out["fused"]["ms_per_step"], "mean_loss": out["fused"]["loss"],
-            "config": "BASELINE.json configs[1]: FFTRefH rank=33 Adagrad bs=500 neg=250, synthetic FB15k-237 shape; fused step "
-                      "(K1 + K3 + loss + adjoints + row-sparse Adagrad, CUDA graph), batch H2D from pinned memory each step",
-            "algorithmic_bytes_per_triple": bytes_per_triple,
-            "hbm_frac": out["fused"]["value"] * bytes_per_triple / 1e9 / 6530.0,
-            "drop_in_contract_loop": {"value": out["drop_in"]["value"], "ms_per_step": out["drop_in"]["ms_per_step"],
-                                      "last_loss": out["drop_in"]["loss"],
-                                      "what": "unfused KGOptimizer loop: 2 model() calls + autograd + dense torch.optim.Adagrad"}}
-
-
-# ------------------------------------------------------------------------------------------------ our arm
-def run_ours(args):
-    import torch.distributed as dist
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank_id = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise RuntimeError("bench.py (our arm) needs a CUDA device: complexhyperbolickge_b200 has no CPU fallback")
-    wd = Watchdog(rank_id)
-    wd.enter("setup (NCCL init, synthetic graph, model, evaluation state)", 300)
-    torch.cuda.set_device(local)
-    device = torch.device("cuda", local)
-    pg = None
-    if world > 1:
-        if world >= 8:
-            # The one 8-GPU run of round 1 hit the harness limit without printing a line (cause unknown).  The path's
-            # collectives are tiny (8 B per query) or plain all_gathers, so the in-switch NVLS algorithms and CUDA-graph
-            # buffer registration buy nothing here: take the plain ring/tree paths at 8 ranks.  Overridable from outside.
-            os.environ.setdefault("NCCL_NVLS_ENABLE", "0")
-            os.environ.setdefault("NCCL_GRAPH_REGISTER", "0")
-        dist.init_process_group("nccl", device_id=device)
-        pg = dist.group.WORLD
-    from argparse import Namespace
-    import complexhyperbolickge_b200 as chk
-    from complexhyperbolickge_b200 import ops, ranking, synthetic
-
-    cfg, model_name, rank = config_dict(args, world)
-    graph = synthetic.make_graph(args.workload, seed=0)
-    n_ent, n_rel2 = graph["n_ent"], graph["n_rel2"]
-    margs = Namespace(sizes=(n_ent, n_rel2, n_ent), rank=rank, dropout=0, gamma=0, dtype=args.dtype, bias="learn",
-                      init_size=1e-3, multi_c=True)
-    with torch.device(device):          # build the 8.2 GB table ON the GPU: no host copy (8 ranks x 12 GB of host RAM), no CPU init
+    margs = Namespace(sizes=(graph["n_ent"], graph["n_rel2"], graph["n_ent"]), rank=rank, dropout=0, gamma=0, dtype=dtype,
+                      bias="learn", init_size=1e-3, multi_c=multi_c)
+    with torch.device(device):          # build the table ON the GPU: no host copy (8 ranks x 12 GB of host RAM at 4M entities), no CPU init
         model = getattr(chk, model_name)(margs)
     model = model.to(device)
     synthetic.trained_like_(model, 0)
-    model.eval()
-    algo = args.rank_algo
-    if algo == "auto":
-        algo = "mma" if ops.mma_available() else "fma"
-    model.rank_algo = algo
-    model.process_group = pg
-    cfg["rank_algo"] = algo
-    b = args.batch
-    K, W = args.steps, args.warmup
+    return model
+
+
+def cycle_batches(ex, n_batches, B):
+    """n_batches batches of B rows from the example set, wrapping around (never slicing past the end)."""
+    idx = (torch.arange(n_batches * B) % ex.shape[0]).view(n_batches, B)
+    return ex[idx]
+
+
+# ------------------------------------------------------------------------------------------------ evaluation
+def measure_eval(model, graph, b, K, W, device, pg, world, rank_id, local, want_e2e, peaks, wd=None):
+    """Filtered full-ranking throughput of `model` on `graph`: resident-input steps (`value`), the dominant kernel alone
+    (roofline) and the public-API call with host buffers (`e2e`).  Returns the pieces of a JSON line (rank 0) or None."""
+    import torch.distributed as dist
+    from complexhyperbolickge_b200 import ops, ranking
+    rank = model.rank
     findex = graph["filters"]["rhs"]
     test = graph["test"]
     reps = (b * (K + W) + len(test) - 1) // len(test)
     qall = np.concatenate([test] * reps)[: b * (K + W)]
-    hist = np.diff(findex.indptr)
-    cfg["filter_len"] = {"mean": float(hist.mean()), "p99": float(np.percentile(hist, 99)), "max": int(hist.max())}
-
-    # ---- resident inputs for `value`
     steps_in = []
     for i in range(K + W):
         qb = qall[i * b:(i + 1) * b]
@@ -472,7 +295,8 @@ def run_ours(args):
                          torch.from_numpy(idx).to(device), int(idx.size)))
     with torch.no_grad():
         state = ranking.eval_state(model)
-        ws = ops.rank_mma_workspace(rank, b, device) if state.algo == ops.CHK_RANK_MMA else None
+        mma = state.algo == ops.CHK_RANK_MMA
+        ws = ops.rank_mma_workspace(rank, b, device) if mma else None
         counts = torch.zeros(b, dtype=torch.int64, device=device)
 
         def step(i):
@@ -482,7 +306,6 @@ def run_ours(args):
             if world > 1:
                 dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=pg)
 
-        wd.enter("evaluation steps (resident inputs) + roofline probe", 180)
         for i in range(W):
             step(i)
         torch.cuda.synchronize()
@@ -515,8 +338,9 @@ def run_ours(args):
 
         # ---- roofline: the dominant kernel alone (rank tile contraction), CUDA events on torch's stream
         qd, ip, ix, tot = steps_in[W]
-        q, _ = ops.query_fwd(model.KIND, rank, True, model.entity.weight.detach(), model.rel.weight.detach(),
-                             model.rel_diag.weight.detach(), None if model._ctx_weight() is None else model._ctx_weight().detach(),
+        ctxw = model._ctx_weight()
+        q, _ = ops.query_fwd(model.KIND, rank, bool(model.multi_c), model.entity.weight.detach(), model.rel.weight.detach(),
+                             model.rel_diag.weight.detach(), None if ctxw is None else ctxw.detach(),
                              model.c.weight.detach(), qd[:, 0].contiguous(), qd[:, 1].contiguous())
         qn = ops.row_hnorm(rank, q)
         bhv = model.bh.weight.detach().view(-1)[qd[:, 0]].contiguous()
@@ -531,7 +355,6 @@ def run_ours(args):
         ops.rank_counts(state.algo, rank, q, qn, bhv, tgt, state.entity, state.hn, state.bt, state.lo, empty_ip, ix, 0,
                         counts, state.shadow, ws)
         call_ms, mma_ms = 0.0, 0.0
-        mma = state.algo == ops.CHK_RANK_MMA
         if mma:                                   # the library records m0/m1 immediately around rank_mma_kernel
             m0.record(); m1.record()
             ops.rank_mma_profile_events(m0, m1)
@@ -550,11 +373,12 @@ def run_ours(args):
         recheck = ops.rank_mma_status(ws) if ws is not None else (0, False)
         shard_rows = state.hi - state.lo
         flops = 8.0 * rank * b * shard_rows
+        algo_name = "mma" if mma else "fma"
+    del state, ws
 
     # ---- e2e through the public API with host buffers
     e2e = None
-    wd.enter("end-to-end get_ranking", 120)
-    if not args.no_e2e:
+    if want_e2e:
         # ONE public-API call over the K timed batches (what compute_metrics does): per batch the host builds the filter
         # CSR, copies ids + CSR host->device from pinned memory and the batch's ranks come back device->host, all
         # inside the timed region; the batches are pipelined (host prepares batch i+1 while the GPU counts batch i).
@@ -580,51 +404,355 @@ def run_ours(args):
         e2e = {"value": b * K / (e_ms * 1e-3), "unit": UNIT, "ranks_equal_resident_path": same, "h2d_bytes_per_step": io["h2d_bytes"] // io["batches"],
                "d2h_bytes_per_step": io["d2h_bytes"] // io["batches"], "ms_per_step": e_ms / K,
                "api": f"model.get_ranking(host LongTensor[{K}*{b},3], FilterIndex, batch_size={b}): one call, {K} pipelined "
-                      "batches, per batch 1 H2D copy (ids + filter CSR, pinned) and 1 D2H copy (ranks)"}
+                      "batches, per batch 1 H2D copy (ids + filter CSR, pinned) and 1 D2H copy (ranks)",
+               "note": "the per-pass evaluation state (Hermitian norms, bf16 shadow: one pass over the table) is cached on the model "
+                       "and was built by the warm call before the timed one; it is rebuilt only after a parameter update"}
+    if rank_id != 0:
+        return None
+    peak_tf = peaks.get("bf16_tflops", 1590.0)
+    achieved = flops / (kern_ms * 1e-3) / 1e12
+    issued = (8 * (rank - 1) * 3 + 8) if mma else 8 * rank
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                "traffic": None,
+                "kernel": "rank_mma_kernel<0,0> (tcgen05 bf16x3 contraction + fused epilogue), timed alone with CUDA events recorded "
+                          "around its launch inside chk_rank_counts" if mma else "rank_tile_kernel (exact FMA tier)",
+                "kernel_ms": kern_ms, "call_ms": call_ms,
+                "call_what": "whole chk_rank_counts call: operand prep + rank_mma_kernel + exact re-check" if mma else "chk_rank_counts",
+                "call_frac": flops / (call_ms * 1e-3) / 1e12 / peak_tf,
+                "algorithmic_flop_per_pair": 8 * rank, "issued_flop_per_pair": issued,
+                "issued_frac": achieved / peak_tf * issued / (8 * rank),
+                "issued_vs_sustained_peak": (achieved * issued / (8 * rank)) / peaks["bf16_tflops_sustained"] if peaks.get("bf16_tflops_sustained") else None,
+                "pairs_per_launch": b * shard_rows, "pairs_per_s": b * shard_rows / (kern_ms * 1e-3),
+                "recheck_pairs_per_launch": recheck[0], "recheck_overflow": recheck[1],
+                "peak_source": ("MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone)" if peaks else "fallback 1.59 PFLOP/s")}
+    hist = np.diff(findex.indptr)
+    return {"value": b * K / (ms_total * 1e-3), "ms_per_step": ms_total / K, "clocks": clocks, "e2e": e2e, "gpu_launches": gpu_launches,
+            "roofline": roofline, "mean_rank_check": float(ranks_check.mean()), "rank_algo": algo_name,
+            "filter_len": {"mean": float(hist.mean()), "p99": float(np.percentile(hist, 99)), "max": int(hist.max())}}
 
-    # ---- the JSON line so far (rank 0); the training legs below only add keys to it
+
+# ------------------------------------------------------------------------------------------------ training
+HBM_GBS_FALLBACK = 6650.0
+
+
+def train_bytes_per_triple(rank, neg, itemsize, double_neg=False):
+    """gathered tail rows + their gradient rows + the query row and its gradient = 2 (2 + neg) 2r s bytes per triple
+    (with double_neg every negative also reads a head row and writes its gradient row: 2 (1 + neg) 2r s more)."""
+    b = 2 * (2 + neg) * 2 * rank * itemsize
+    if double_neg:
+        b += 2 * (1 + neg) * 2 * rank * itemsize
+    return b
+
+
+def measure_train(model, graph, opt_name, lr, B, neg, double_neg, steps, warmup, device, pg, world, peaks, contract_steps=0):
+    """Training throughput through the public optimizer API: FusedKGOptimizer.fused_step (world 1) or
+    FusedDataParallelKGOptimizer.step (global batch B*world, weak scaling).  Every step's batch comes from pinned host memory
+    (H2D inside the timed region); the mean loss is read back once after the timed steps."""
+    import torch.distributed as dist
+    from complexhyperbolickge_b200 import ops, synthetic
+    from complexhyperbolickge_b200.optim import KGOptimizer, N3
+    from complexhyperbolickge_b200.parallel import FusedDataParallelKGOptimizer
+    from complexhyperbolickge_b200.train import FusedKGOptimizer
+    model.train()
+    mk = {"Adagrad": lambda ps: torch.optim.Adagrad(ps, lr=lr), "Adam": lambda ps: torch.optim.Adam(ps, lr=lr)}[opt_name]
+    Bg = B * world
+    torch_opt = mk(model.parameters())
+    if world > 1:
+        opt = FusedDataParallelKGOptimizer(model, N3(0.0), torch_opt, Bg, 1, neg, double_neg, verbose=False, process_group=pg,
+                                           use_cuda_graph=os.environ.get("CHK_DP_GRAPH", "1") != "0")
+    else:
+        opt = FusedKGOptimizer(model, N3(0.0), torch_opt, Bg, 1, neg, double_neg, verbose=False)
+    ex = synthetic.train_examples(graph)
+    ex = ex[torch.randperm(ex.shape[0], generator=torch.Generator().manual_seed(0))]
+    pinned = cycle_batches(ex, steps + warmup, Bg).pin_memory()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0, first = 0, ops.launch_count
+    kernels_per_step = None
+    for i in range(steps + warmup):
+        if i == 1:                                                    # step 0 ran every wrapper once (twice when it also captured the graph)
+            kernels_per_step = (ops.launch_count - first) / (2 if opt.use_cuda_graph else 1)
+        if i == warmup:
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            opt._loss_sum.zero_()
+            launches0 = ops.launch_count
+            ev0.record()
+        if world > 1:
+            opt.step(pinned[i])                                       # rows rank::world, H2D inside
+        else:
+            opt.fused_step(pinned[i].to(device, non_blocking=True))
+    launches = ops.launch_count - launches0
+    lv = opt._loss_sum.double()
+    if world > 1:
+        dist.all_reduce(lv, op=dist.ReduceOp.SUM, group=pg)
+    lv = lv.item() / steps                                            # D2H of the result inside the timed region
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / steps
+    if world > 1:
+        t = torch.tensor([ms], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    es = model.entity.weight.element_size()
+    bpt = train_bytes_per_triple(model.rank, neg, es, double_neg)
+    hbm = peaks.get("hbm_gbs", HBM_GBS_FALLBACK)
+    out = {"metric": "train_triples_per_sec", "value": Bg / (ms * 1e-3), "unit": "triples/s", "ms_per_step": ms, "scaling": "weak",
+           "global_batch": Bg, "mean_loss": lv, "optimizer": opt_name, "neg": neg, "double_neg": bool(double_neg),
+           "kernels_per_step": kernels_per_step, "eager_launches_in_timed_region": launches,
+           "h2d_bytes_per_step": (Bg // world) * 24, "d2h_bytes_total": 8,
+           "algorithmic_bytes_per_triple": bpt,
+           "hbm_frac_per_gpu": (Bg / world) / (ms * 1e-3) * bpt / 1e9 / hbm,
+           "path": ("FusedDataParallelKGOptimizer.step: fused chain per rank on rows rank::world (CUDA graph incl. NCCL), "
+                    + ("sparse row exchange: all_gather of slot ids + contribution rows, one-kernel ordered reduce + Adagrad in place"
+                       if getattr(opt, "sparse_entity", False) else "local segment-reduce into a flat dense gradient + ONE all_reduce + dense apply")
+                    if world > 1 else
+                    "FusedKGOptimizer.fused_step: prep(sampler) -> K1 -> K3 fwd+loss+bwd -> K1 adjoint -> ordered segment-reduce + optimizer (CUDA graph)")}
+    if world > 1 and getattr(opt, "sparse_entity", False):
+        pl = opt._plan(opt.local_batch_size)
+        nbytes = pl.flat.numel() * es + pl.ent_ids.numel() * 8
+        out["exchange_bytes_in_per_rank_per_step"] = (world - 1) * nbytes
+        out["exchange_gbs_in_per_rank"] = (world - 1) * nbytes / (ms * 1e-3) / 1e9
+        out["nvlink_ref_gbs"] = 770.0
+    if contract_steps:
+        del opt
+        m2 = model
+        c_opt = KGOptimizer(m2, N3(0.0), mk(m2.parameters()), B, 1, neg, double_neg, verbose=False)
+        for p in m2.parameters():
+            p.grad = None
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        loss = None
+        for i in range(contract_steps + 2):
+            if i == 2:
+                torch.cuda.synchronize()
+                c0.record()
+            bb = pinned[i % pinned.shape[0]][:B].to(device, non_blocking=True)
+            loss = c_opt.calculate_loss(bb)
+            loss.backward()
+            c_opt.optimizer.step()
+            c_opt.optimizer.zero_grad()
+        last = loss.item()
+        c1.record()
+        torch.cuda.synchronize()
+        cms = c0.elapsed_time(c1) / contract_steps
+        out["drop_in_contract_loop"] = {"value": B / (cms * 1e-3), "ms_per_step": cms, "last_loss": last,
+                                        "what": "unfused KGOptimizer loop: 2 model() calls + autograd + dense torch.optim"}
+    for p in model.parameters():
+        p.grad = None
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ kernel rooflines
+_FLUSH = None
+
+
+def _time_kernel(fn, reps=5):
+    """Median CUDA-event time of fn() on torch's current stream, L2 flushed (256 MB write) between repetitions."""
+    global _FLUSH
+    if _FLUSH is None:
+        _FLUSH = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        _FLUSH.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return float(np.median(ts))
+
+
+def kernel_rooflines(device, peaks):
+    """K1 (query transform) and K3 (training pass) alone at sizes where they are not launch-latency bound, against the
+    measured HBM copy bandwidth.  Algorithmic bytes as in DESIGN.md §4."""
+    from complexhyperbolickge_b200 import ops
+    hbm = peaks.get("hbm_gbs", HBM_GBS_FALLBACK)
+    src = "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s"
+    g = torch.Generator(device=device).manual_seed(0)
+    out = {}
+    f32 = torch.float32
+    # ---- K1 at 2^20 queries, rank 33 fp32 (entity table 1M rows = 264 MB > L2)
+    rank, nq, n_ent, n_rel2 = 33, 1 << 20, 1_000_000, 474
+    n = 2 * (rank - 1)
+    ent = torch.randn(n_ent, 2 * rank, generator=g, device=device, dtype=f32) * float(np.sqrt(0.4 / (2 * rank)))
+    rel = torch.randn(n_rel2, 2 * n, generator=g, device=device, dtype=f32) * 0.05
+    rd = torch.rand(n_rel2, n, generator=g, device=device, dtype=f32) * 2 - 1
+    c = torch.rand(n_rel2, 1, generator=g, device=device, dtype=f32) + 0.5
+    h = torch.randint(0, n_ent, (nq,), generator=g, device=device)
+    r = torch.randint(0, n_rel2, (nq,), generator=g, device=device)
+    q_out = torch.empty(nq, 2 * rank, device=device, dtype=f32)
+    c_out = torch.empty(nq, device=device, dtype=f32)
+    byt = nq * (2 * 2 * rank * 4 + 16)
+    ms_lane = _time_kernel(lambda: ops.query_fwd(ops.CHK_ROT, rank, True, ent, rel, rd, None, c, h, r, grouped=False, out=(q_out, c_out)))
+    ms_tpq = _time_kernel(lambda: ops.query_fwd(ops.CHK_ROT, rank, True, ent, rel, rd, None, c, h, r, grouped=True, out=(q_out, c_out)))
+    best = min(ms_lane, ms_tpq)
+    out["roofline_k1"] = {"bound": "hbm", "achieved": byt / best / 1e6, "peak": hbm, "unit": "GB/s", "frac": byt / best / 1e6 / hbm, "traffic": None,
+                          "kernel": "K1 query transform forward (FFTRotH rank 33 fp32, 2^20 queries, 1M-entity table), best of the lane-group kernel "
+                                    "and the thread-per-query kernel incl. its counting sort by relation",
+                          "ms_lane_group": ms_lane, "ms_thread_per_query": ms_tpq, "algorithmic_bytes_per_query": 2 * 2 * rank * 4 + 16,
+                          "queries_per_launch": nq, "peak_source": src}
+    gq = torch.randn(nq, 2 * rank, generator=g, device=device, dtype=f32)
+    bufs = [torch.empty(nq, w, device=device, dtype=f32) for w in (2 * rank, 2 * n, n)] + [None, torch.empty(nq, device=device, dtype=f32)]
+    bytb = nq * ((2 * 2 * rank + 2 * rank + 2 * n + n + 1) * 4 + 16)
+    ms_b = _time_kernel(lambda: ops.query_bwd_into(ops.CHK_ROT, rank, True, ent, rel, rd, None, c, h, r, gq, *bufs))
+    out["roofline_k1_bwd"] = {"bound": "hbm", "achieved": bytb / ms_b / 1e6, "peak": hbm, "unit": "GB/s", "frac": bytb / ms_b / 1e6 / hbm,
+                              "traffic": None, "kernel": "K1 adjoint (lane-group kernel), same shape", "kernel_ms": ms_b,
+                              "algorithmic_bytes_per_query": bytb // nq, "peak_source": src}
+    del gq, bufs, q_out, c_out
+    # ---- K3 training pass at B = 4096 (rank 33, neg 250) and B = 2048 (rank 257, neg 100)
+    for key, rank, B, neg, n_ent in (("roofline_k3", 33, 4096, 250, 1_000_000), ("roofline_k3_r257", 257, 2048, 100, 1_000_000)):
+        nt = neg + 1
+        ent = torch.randn(n_ent, 2 * rank, generator=g, device=device, dtype=f32) * float(np.sqrt(0.4 / (2 * rank)))
+        bh = torch.randn(n_ent, generator=g, device=device, dtype=f32) * 0.1
+        bt = torch.randn(n_ent, generator=g, device=device, dtype=f32) * 0.1
+        q = ent[torch.randint(0, n_ent, (B,), generator=g, device=device)].contiguous()
+        heads = torch.randint(0, n_ent, (B,), generator=g, device=device)
+        tails = torch.randint(0, n_ent, (B, nt), generator=g, device=device)
+        hyper = torch.tensor([0.1, 1e-10, 1.0 / (B * nt), float(B), 0, 0, 1.0 / B, 0], dtype=torch.float64, device=device)
+        lp, gs = torch.empty(B, device=device, dtype=f32), torch.empty(B, nt, device=device, dtype=f32)
+        gq, grow, gbh = torch.empty(B, 2 * rank, device=device, dtype=f32), torch.empty(B * nt, 2 * rank, device=device, dtype=f32), torch.empty(B, device=device, dtype=f32)
+        ms3 = _time_kernel(lambda: ops.score_gather_train(rank, B, nt, q, 1, 0, ent, tails, heads, 1, 0, bh, bt, hyper, lp, gs, gq, grow, gbh))
+        by3 = B * train_bytes_per_triple(rank, neg, 4)
+        out[key] = {"bound": "hbm", "achieved": by3 / ms3 / 1e6, "peak": hbm, "unit": "GB/s", "frac": by3 / ms3 / 1e6 / hbm, "traffic": None,
+                    "kernel": f"K3 training pass chk_score_gather_train (scores + loss + adjoint, tail rows gathered once), rank {rank} fp32, "
+                              f"B={B}, neg={neg}, 1M-entity table", "kernel_ms": ms3,
+                    "algorithmic_bytes_per_triple": by3 // B, "triples_per_launch": B, "peak_source": src}
+        del ent, bh, bt, q, tails, grow
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ per-config legs
+SMALL_CONFIGS = [
+    # key, BASELINE.json index, workload, model, rank, dtype, train (optimizer, lr, neg, double_neg) or None
+    ("configs[0]", 0, "wn18rr", "FFTRotH", 33, "float", ("Adam", 3e-4, 100, True)),
+    ("configs[1]", 1, "fb237", "FFTRefH", 33, "float", ("Adagrad", 0.02, 250, False)),
+    ("configs[2]", 2, "yago310", "FFTAttH", 33, "float", ("Adagrad", 0.02, 100, False)),
+    ("configs[3]", 3, "wn18rr", "FFTRotH", 65, "double", None),
+]
+
+
+def small_config_legs(device, peaks, K, W, graphs, only=None):
+    """BASELINE.json configs[0..3] on one GPU: filtered-eval queries/s (resident + e2e, own roofline entry) and, where the
+    config names a training setup, triples/s through FusedKGOptimizer.  configs[3] (--dtype double) also states rank equality
+    between the tensor-core tier (bf16x3 prefilter + fp64 re-check), the exact fp64 FMA tier and the CPU oracle."""
+    from complexhyperbolickge_b200 import synthetic
+    out = []
+    for key, idx, workload, model_name, rank, dtype, train in SMALL_CONFIGS:
+        if only is not None and idx not in only:
+            continue
+        if workload not in graphs:
+            graphs[workload] = synthetic.make_graph(workload, seed=0)
+        graph = graphs[workload]
+        model = make_model(model_name, rank, dtype, graph, device)
+        model.eval()
+        entry = {"config": key, "workload": f"{model_name} rank={rank} {dtype}, synthetic {workload} ({graph['n_ent']} entities, "
+                                            f"{graph['n_rel2'] // 2} relations), eval batch 500"}
+        ev = measure_eval(model, graph, 500, K, W, device, None, 1, 0, 0, True, peaks)
+        entry["eval"] = {"metric": METRIC, "unit": UNIT, **{k: ev[k] for k in ("value", "ms_per_step", "e2e", "roofline", "rank_algo", "gpu_launches", "mean_rank_check")}}
+        if dtype == "double":
+            entry["eval"]["fp64_check"] = fp64_rank_check(model, graph, model_name, rank)
+        model.release_eval_cache()
+        if train is not None:
+            opt_name, lr, neg, dn = train
+            entry["train"] = measure_train(model, graph, opt_name, lr, 500, neg, dn, 20 * K, 3, device, None, 1, peaks,
+                                           contract_steps=10 if idx == 1 else 0)
+        out.append(entry)
+        del model
+        torch.cuda.empty_cache()
+    return out
+
+
+def fp64_rank_check(model, graph, model_name, rank, n_q=24):
+    """configs[3]: ranks of the tensor-core tier == ranks of the exact fp64 FMA tier on 500 queries, and == the CPU oracle
+    (fp64 restatement of the reference) on n_q queries; the oracle call doubles as this config's CPU baseline."""
+    from complexhyperbolickge_b200 import synthetic
+    from oracle import chk_oracle as O
+    test = torch.from_numpy(graph["test"][:500])
+    findex = graph["filters"]["rhs"]
+    keep = model.rank_algo
+    model.rank_algo = "mma"
+    r_mma = model.get_ranking(test, findex, batch_size=500)
+    model.rank_algo = "fma"
+    r_fma = model.get_ranking(test, findex, batch_size=500)
+    model.rank_algo = keep
+    model.release_eval_cache()
+    p = O.Params.from_state_dict({k: v.detach().cpu() for k, v in model.state_dict().items()}, O.KIND[model_name], rank, True)
+    qs = test[:n_q]
+    fd = synthetic.filter_dict(findex)
+    filters = {(int(h), int(r)): fd[(int(h), int(r))] for h, r, _ in qs.tolist()}
+    torch.set_num_threads(os.cpu_count())
+    t0 = time.perf_counter()
+    r_or = O.get_ranking(p, qs, filters, batch_size=8)
+    dt = time.perf_counter() - t0
+    return {"ranks_mma_equal_exact_fp64_tier": bool(torch.equal(r_mma, r_fma)), "ranks_equal_cpu_oracle_fp64": bool(torch.equal(r_mma[:n_q], r_or)),
+            "queries_checked": [500, n_q],
+            "cpu_baseline": {"value": n_q / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                             "sample": f"{n_q} queries against all {graph['n_ent']} entities, {dt:.1f} s of CPU work (oracle port, fp64)"}}
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank_id = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (our arm) needs a CUDA device: complexhyperbolickge_b200 has no CPU fallback")
+    wd = Watchdog(rank_id)
+    wd.enter("setup (NCCL init, synthetic graph, model, evaluation state)", 300)
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    pg = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+        pg = dist.group.WORLD
+    from complexhyperbolickge_b200 import ops, synthetic
+
+    peaks = load_peaks()
+    cfg, model_name, rank = config_dict(args, world)
+    graphs = {args.workload: synthetic.make_graph(args.workload, seed=0)}
+    graph = graphs[args.workload]
+    n_ent, n_rel2 = graph["n_ent"], graph["n_rel2"]
+    model = make_model(model_name, rank, args.dtype, graph, device)
+    model.eval()
+    algo = args.rank_algo
+    if algo == "auto":
+        algo = "mma" if ops.mma_available() else "fma"
+    model.rank_algo = algo
+    model.process_group = pg
+    b, K, W = args.batch, args.steps, args.warmup
+
+    wd.enter("evaluation steps (resident inputs) + roofline probe + end-to-end get_ranking", 300)
+    ev = measure_eval(model, graph, b, K, W, device, pg, world, rank_id, local, not args.no_e2e, peaks, wd)
+
+    # ---- the JSON line so far (rank 0); the legs below only add keys to it
     line = None
     if rank_id == 0:
-        peaks = {}
-        pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.exists(pk):
-            peaks = json.load(open(pk))
-        peak_tf = peaks.get("bf16_tflops", 1590.0)
-        achieved = flops / (kern_ms * 1e-3) / 1e12
-        traffic = None                  # dram bytes per launch of the dominant kernel, from the committed ncu --set full capture
         tp = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tp) and world == 1 and args.workload == "big4m" and mma:
-            traffic = json.load(open(tp)).get("rank_mma_kernel_big4m_dram_bytes_per_launch")
-        issued = (8 * (rank - 1) * 3 + 8) if mma else 8 * rank
-        roofline = {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                    "traffic": traffic,
-                    "kernel": "rank_mma_kernel<0,0> (tcgen05 bf16x3 contraction + fused epilogue), timed alone with CUDA events recorded "
-                              "around its launch inside chk_rank_counts" if mma else "rank_tile_kernel<float,1> (fp32 FMA)",
-                    "kernel_ms": kern_ms, "call_ms": call_ms,
-                    "call_what": "whole chk_rank_counts call: operand prep + rank_mma_kernel + exact re-check" if mma else "chk_rank_counts",
-                    "call_frac": flops / (call_ms * 1e-3) / 1e12 / peak_tf,
-                    "algorithmic_flop_per_pair": 8 * rank, "issued_flop_per_pair": issued,
-                    "issued_frac": achieved / peak_tf * issued / (8 * rank),
-                    "issued_vs_sustained_peak": (achieved * issued / (8 * rank)) / peaks["bf16_tflops_sustained"] if peaks.get("bf16_tflops_sustained") else None,
-                    "pairs_per_launch": b * shard_rows, "recheck_pairs_per_launch": recheck[0], "recheck_overflow": recheck[1],
-                    "peak_source": ("MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone)" if peaks else "fallback 1.59 PFLOP/s")}
-        line = {"metric": METRIC, "value": b * K / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-                "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-                "dtype": "f32" if args.dtype == "float" else "f64", "data": "synthetic", "config": cfg, "clocks": clocks,
-                "e2e": e2e, "gpu_launches": gpu_launches, "roofline": roofline,
-                "mean_rank_check": float(ranks_check.mean())}
+        if os.path.exists(tp) and world == 1 and args.workload == "big4m" and ev["rank_algo"] == "mma":
+            ev["roofline"]["traffic"] = json.load(open(tp)).get("rank_mma_kernel_big4m_dram_bytes_per_launch")
+        line = {"metric": METRIC, "value": ev["value"], "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ev["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32" if args.dtype == "float" else "f64", "data": "synthetic", "config": cfg, "clocks": ev["clocks"],
+                "e2e": ev["e2e"], "gpu_launches": ev["gpu_launches"], "roofline": ev["roofline"],
+                "mean_rank_check": ev["mean_rank_check"], "rank_algo": ev["rank_algo"], "filter_len": ev["filter_len"],
+                "train_examples_in_graph": int(graph["train"].shape[0]) * 2}
         wd.partial = line
 
     # ---- training legs (every rank takes part); each has its own deadline, a stuck leg is reported, not waited for
-    del state, ws
     model.release_eval_cache()
+    model.process_group = None
     torch.cuda.empty_cache()
-    def leg(key, what, seconds, fn, *a):
-        """A training leg adds a key to the line; if it fails the headline (evaluation) numbers are still reported."""
+
+    def leg(key, what, seconds, fn, *a, **kw):
+        """A leg adds a key to the line; if it fails the headline (evaluation) numbers are still reported."""
         import traceback
         wd.enter(what, seconds)
         try:
-            out = fn(*a)
+            out = fn(*a, **kw)
         except Exception as e:                       # noqa: BLE001 — reported in the line, stack on stderr
             traceback.print_exc(file=sys.stderr)
             out = {"error": f"{type(e).__name__}: {e}"[:400]}
@@ -632,20 +760,35 @@ def run_ours(args):
             line[key] = out
 
     if not args.no_train:
-        if world > 1:
-            leg("train", "data-parallel training leg (configs[1] shape)", 120, dp_train_leg, 20, 3, device, pg, world)
         if args.workload == "big4m":
-            leg("train_big4m", "training leg on the 4M-entity table (configs[4])", 180, train_big_leg, model, graph, 50, 5,
-                device, pg, world)
+            leg("train_big4m", "training leg on the 4M-entity table (configs[4])", 240, measure_train, model, graph, "Adagrad", 0.02,
+                500, 100, False, 50, 5, device, pg, world, peaks)
+            if line is not None and "error" not in line["train_big4m"]:
+                line["train_big4m"]["config"] = (f"BASELINE.json configs[4]: FFTRotH rank={rank} Adagrad, 500 triples per rank x{world}, neg=100, "
+                                                 "synthetic 4M-entity graph, replicated tables")
     del model
     torch.cuda.empty_cache()
-    if rank_id != 0:
+    if not args.no_train:
+        def cfg1_train():
+            if "fb237" not in graphs:
+                graphs["fb237"] = synthetic.make_graph("fb237", seed=0)
+            m1 = make_model("FFTRefH", 33, "float", graphs["fb237"], device)
+            out = measure_train(m1, graphs["fb237"], "Adagrad", 0.02, 500, 250, False, 200, 5, device, pg, world, peaks,
+                                contract_steps=10 if world == 1 else 0)
+            out["config"] = f"BASELINE.json configs[1]: FFTRefH rank=33 Adagrad neg=250, 500 triples per rank x{world}, synthetic FB15k-237 shape"
+            return out
+        leg("train", "training leg (configs[1] shape)", 180, cfg1_train)
+    if world > 1:
         wd.enter("process-group teardown", 30)
-        dist.destroy_process_group()
-        wd.stop()
-        return
-    if world == 1 and not args.no_train:
-        leg("train", "single-GPU training leg (configs[1])", 240, train_leg, 20, 3, device)
+        if rank_id != 0:
+            dist.destroy_process_group()
+            wd.stop()
+            return
+    if world == 1 and not args.no_configs:
+        leg("configs", "BASELINE.json configs[0..3] (eval + train per config)", 420, small_config_legs, device, peaks, K, W, graphs)
+        leg("kernel_rooflines", "K1 / K3 kernel rooflines", 120, kernel_rooflines, device, peaks)
+        if "error" not in line["kernel_rooflines"]:
+            line.update(line.pop("kernel_rooflines"))
     if world == 1 and not args.no_cpu_baseline:
         wd.enter("CPU baseline (oracle port on the host cores)", 300)
         v, spent, sample = oracle_eval_budget(model_name, rank, args.dtype, n_ent, n_rel2, budget_s=12.0)
@@ -654,7 +797,6 @@ def run_ours(args):
             line["train"]["cpu_baseline"] = oracle_train_sample()
     wd.emit(line)
     if world > 1:
-        wd.enter("process-group teardown", 30)
         dist.destroy_process_group()
     wd.stop()
 

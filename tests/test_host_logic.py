@@ -147,9 +147,9 @@ def _load_bench():
     return mod
 
 
-def test_bench_watchdog_emits_partial_line_and_exits_zero():
+def test_bench_watchdog_emits_partial_line_and_exits_nonzero():
     """A phase that exceeds its deadline must not hang the job: stacks to stderr, the line measured so far + "error" on
-    stdout (rank 0), exit code 0."""
+    stdout (rank 0), and a NON-zero exit code (3): a hung phase is a failure even though the partial line is kept."""
     import subprocess
     import sys
     code = ("import sys, time, importlib.util\n"
@@ -159,7 +159,7 @@ def test_bench_watchdog_emits_partial_line_and_exits_zero():
             "wd.enter('fake stuck phase', 1); time.sleep(20); print('NOT REACHED')\n")
     for rank, expect_line in ((0, True), (3, False)):
         r = subprocess.run([sys.executable, "-c", code, str(rank)], capture_output=True, text=True, timeout=60)
-        assert r.returncode == 0 and "NOT REACHED" not in r.stdout
+        assert r.returncode == 3 and "NOT REACHED" not in r.stdout
         assert "fake stuck phase" in r.stderr
         if expect_line:
             import json
@@ -185,3 +185,13 @@ def test_bench_reference_arm_prints_one_json_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_bench_cycles_examples_instead_of_slicing_past_the_end():
+    """r1 N=8 hang: the DP leg sliced 812,000 rows out of 544,230 examples, so late steps got short / empty batches and the
+    ranks issued collectives of different sizes.  Batches now wrap around: every batch has exactly B rows."""
+    bench = _load_bench()
+    ex = torch.arange(30).view(10, 3)
+    out = bench.cycle_batches(ex, 7, 4)
+    assert out.shape == (7, 4, 3)
+    assert torch.equal(out.view(-1, 3)[:10], ex) and torch.equal(out.view(-1, 3)[10:20], ex)

@@ -121,8 +121,9 @@ def main():
             dist.all_reduce(lsum)
             if rank == 0:
                 print(f"[fused dp {name} r={r} {dtype} x{world} {'sparse rows' if sparse else 'dense'}] 4 steps: loss single "
-                      f"{f1._loss_sum.item() / 4:.9f} mean-of-ranks {lsum.item() / world / 4:.9f}  max |param diff| / max|param| = "
+                      f"{f1._loss_sum.item() / 4:.9f} sum-over-ranks {lsum.item() / 4:.9f}  max |param diff| / max|param| = "
                       f"{worst:.2e}  max replica divergence = {replica:.1e}", flush=True)
+            assert abs(f1._loss_sum.item() - lsum.item()) / 4 < (1e-10 if dtype == "double" else 1e-4)
             assert worst < (1e-9 if dtype == "double" else 5e-3)     # fp32: Adagrad normalises tiny early gradients
             assert replica == 0.0
             del f1, f2
