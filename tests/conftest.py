@@ -52,3 +52,25 @@ def filters_from_arrays(case):
         out[side] = {(int(k[0]), int(k[1])): [int(v) for v in vals[indptr[i]:indptr[i + 1]]]
                      for i, k in enumerate(keys)}
     return out
+
+
+# ---- observed parity margins: every GPU parity test records its worst observed error; written once per session to
+# gpurun_out/parity_observed.json (the directory that travels back from the GPU box) and committed under profiles/.
+_PARITY = {}
+
+
+def record_parity(key, **vals):
+    slot = _PARITY.setdefault(key, {})
+    for k, v in vals.items():
+        v = float(v)
+        slot[k] = max(slot.get(k, v), v)
+
+
+def pytest_sessionfinish(session, exitstatus):
+    if not _PARITY:
+        return
+    import json
+    out = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, "parity_observed.json"), "w") as f:
+        json.dump(_PARITY, f, indent=1, sort_keys=True)

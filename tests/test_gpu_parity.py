@@ -1,12 +1,16 @@
 """GPU parity (pytest -m gpu): the CUDA path, called through the C ABI (ops -> libchk_b200.so), against
 (1) golden vectors produced by the reference itself and (2) the CPU oracle on seeded inputs.
 
-Stated tolerances (north_star: 1e-5 relative in fp32, 1e-12 in --dtype double, plus the conditioning term
-of SURVEY §7 hard part A — the score is a function of x-1 where x ~ 1 + d^2/2 is computed with
-cancellation, so even reference-vs-reference with another summation order moves by eps_mach * x / (x-1)):
-  values  : |got-ref| <= rtol * max|ref|,  rtol = 1e-11 (fp64 q), 1e-9 (fp64 scores), 3e-5 / 2e-3 (fp32)
+Stated tolerances (north_star: 1e-5 relative in fp32, 1e-12 in --dtype double, plus the conditioning term of SURVEY §7
+hard part A):
+  scores  : PER ELEMENT  |got - truth| <= K_SCORE * eps_machine * unit,  unit = 2(x+1)(1 + 1/|zn| + 1/|wn|) + |s| + |bh| + |bt|
+            (tests/parity_units.py; truth = the oracle in fp64 on the same weights with the model's clamp constant), and the flat
+            north-star check |got - ref| <= rtol * max|ref| against the reference's own fixture values;
+  queries : |got-ref| <= rtol * max|ref|,  rtol = 1e-11 (fp64), 3e-5 (fp32)
   grads   : 2e-8 (fp64), 2e-2 (fp32), 0.2 (fp32 boundary regime: O(1/eps) conditioning)
-  ranks   : identical in fp64; fp32: |d rank| <= 2 on < 3 % of queries (near-ties)
+  ranks   : identical in fp64; fp32: |rank - fp64 rank| <= #{entities whose fp64 score is within the two error bands of the
+            target's} per query, on BOTH ranking tiers (exact FMA tier and tcgen05 tier).
+The worst observed value of every check is recorded (conftest.record_parity -> profiles/parity_r2.json).
 """
 from argparse import Namespace
 
@@ -14,9 +18,18 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import filters_from_arrays, golden_files, load_case, oracle_params
+from conftest import filters_from_arrays, golden_files, load_case, oracle_params, record_parity
 
 pytestmark = pytest.mark.gpu
+
+K_SCORE = 16           # multiples of eps_machine * unit allowed per score element; the reference's own fp32 / fp64 outputs sit at 0.1-1.1 (profiles/parity_r2.json)
+K_BAND = 16            # half-width of the near-tie band of the fp32 rank bound, same units
+
+
+def _observed(a, b):
+    a = a.detach().cpu().double().numpy() if isinstance(a, torch.Tensor) else np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return float(np.abs(a - b.reshape(a.shape)).max() / max(np.abs(b).max(), 1e-300))
 
 
 def _model_from_case(case, prefix="p_", device="cuda"):
@@ -59,6 +72,19 @@ def test_step_vs_reference_golden(path):
     ngs, _ = model(batch[:, :2].unsqueeze(1), neg)
     _close(pos, case["score_pos"], st, "positive scores")
     _close(ngs, case["score_neg"], st, "negative scores")
+    # conditioning-aware, per element, against the fp64 truth on the same weights
+    import parity_units as PU
+    p = oracle_params(case)
+    mdt = torch.float64 if dbl else torch.float32
+    bt_, nt_ = torch.from_numpy(case["batch"]), torch.from_numpy(case["neg"])
+    truth, unit = PU.pair_truth(p, bt_[:, 0], bt_[:, 1], torch.cat((bt_[:, 2:3], nt_), 1))
+    got_all = torch.cat((pos.detach().reshape(-1, 1), ngs.detach().reshape(nt_.shape)), 1)
+    ru = PU.ratio(got_all, truth, unit, mdt)
+    tag = f"{'fp64' if dbl else 'fp32'}/{case['regime']}"
+    record_parity("step_scores_units/" + tag, max_err_in_eps_units=ru)
+    record_parity("step_scores_rel/" + tag, max_rel_to_max=max(_observed(pos, case["score_pos"]), _observed(ngs, case["score_neg"])))
+    record_parity("step_queries_rel/" + tag, max_rel_to_max=_observed(q, case["q"]))
+    assert ru <= K_SCORE, f"score error {ru:.1f} eps-units > {K_SCORE}"
     lsig = torch.nn.functional.logsigmoid
     loss = -torch.cat([lsig(pos).view(-1), lsig(-ngs).view(-1)]).mean()
     loss.backward()
@@ -73,6 +99,7 @@ def test_step_vs_reference_golden(path):
             assert got.abs().max().item() <= 1e-30, k
         else:
             _close(got, ref, gt, "grad " + k)
+            record_parity("step_grads_rel/" + tag, max_rel_to_max=_observed(got, ref))
     # the unfused API path (get_queries / get_rhs / score with autograd) must agree with the fused forward
     model.zero_grad()
     model.fused_forward = False
@@ -87,23 +114,35 @@ def test_step_vs_reference_golden(path):
             _close(p.grad, ref, gt, "unfused grad " + k)
 
 
+@pytest.mark.parametrize("algo", ["fma", "mma"])
 @pytest.mark.parametrize("path", golden_files("rank_"), ids=lambda p: p.split("/")[-1][5:-4])
-def test_ranking_vs_reference_golden(path):
+def test_ranking_vs_reference_golden(path, algo):
+    """Filtered ranks of both tiers against the ranks the REFERENCE computed (fixtures).  fp64: identical.  fp32: the
+    reference's fp32 ranks and ours may each differ from the fp64 truth by the near-tie count of the query, so they may differ
+    from each other by at most twice that count."""
+    import parity_units as PU
     case = load_case(path)
     model = _model_from_case(case)
     model.eval()
+    model.rank_algo = algo
     filters = filters_from_arrays(case)
     ex = torch.from_numpy(case["test"])
     ranks = model.get_ranking(ex, filters["rhs"], batch_size=37)
     q = torch.stack([ex[:, 2], ex[:, 1] + case["n_rel2"] // 2, ex[:, 0]], -1)
     ranks_l = model.get_ranking(q, filters["lhs"], batch_size=500)
     assert ranks.dtype == torch.float32 and ranks.shape == (ex.shape[0],)
-    for got, ref in ((ranks.numpy(), case["ranks_rhs"]), (ranks_l.numpy(), case["ranks_lhs"])):
+    p = oracle_params(case)
+    for side, qs, got, ref in (("rhs", ex, ranks.numpy(), case["ranks_rhs"]), ("lhs", q, ranks_l.numpy(), case["ranks_lhs"])):
         if case["dtype"] == "double":
             assert np.array_equal(got, ref), np.abs(got - ref).max()
         else:
+            truth, near = PU.rank_band_counts(p, qs, filters[side], K_BAND)
+            d_truth = np.abs(got - truth.numpy())
+            assert (d_truth <= near.numpy()).all(), (d_truth.max(), near.max().item())
             d = np.abs(got - ref)
-            assert d.max() <= 2 and (d > 0).mean() < 0.03, (d.max(), (d > 0).mean())
+            assert (d <= 2 * near.numpy()).all(), (d.max(), near.max().item())
+            record_parity(f"rank_golden_fp32/{algo}/{case['regime']}", max_abs_rank_diff_vs_reference=d.max(), frac_queries_differing=(d > 0).mean(),
+                          max_abs_rank_diff_vs_fp64_truth=d_truth.max())
     mr, mrr, hits = model.compute_metrics(ex, filters, batch_size=64)
     tol = 1e-6 if case["dtype"] == "double" else 2e-2
     assert abs(mr["rhs"] - case["mr"][0]) <= tol * case["mr"][0]
@@ -193,22 +232,32 @@ def test_step_vs_oracle_all_ranks(name, rank, dtype):
     loss.backward()
     dbl = dtype == torch.float64
     assert abs(loss.item() - loss_ref.item()) <= (1e-12 if dbl else 2e-5)
+    import parity_units as PU
+    truth, unit = PU.pair_truth(p, batch[:, 0], batch[:, 1], torch.cat((batch[:, 2:3], negs), 1))
+    ru = PU.ratio(s.detach().reshape(truth.shape), truth, unit, dtype)
+    record_parity(f"oracle_scores_units/{'fp64' if dbl else 'fp32'}/r{rank}", max_err_in_eps_units=ru)
+    assert ru <= K_SCORE, f"score error {ru:.1f} eps-units > {K_SCORE}"
     for k, gr in grads_ref.items():
         got = getattr(model, k).weight.grad
         _close(got, gr.numpy(), 2e-9 if dbl else 2e-2, f"grad {k}")
+        record_parity(f"oracle_grads_rel/{'fp64' if dbl else 'fp32'}/r{rank}", max_rel_to_max=_observed(got, gr.numpy()))
     q_ref, _ = O.query_fwd(p, batch[:, 0], batch[:, 1])
     (q, _c), _ = model.get_queries(bc[:, :2])
     _close(q.squeeze(1), q_ref.numpy(), 1e-12 if dbl else 3e-5, "get_queries")
 
 
+@pytest.mark.parametrize("algo", ["fma", "mma"])
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
 @pytest.mark.parametrize("name,rank", [("FFTRotH", 33), ("FFTRefH", 65), ("FFTAttH", 33), ("FFTRotH", 257)])
-def test_ranking_vs_oracle(name, rank, dtype):
-    """Filtered ranks on a seeded graph with heavy (Zipf) filters vs the oracle; double_neg-shaped queries too."""
+def test_ranking_vs_oracle(name, rank, dtype, algo):
+    """Filtered ranks of both tiers on a seeded graph with heavy (Zipf) filters vs the oracle.  fp64: identical.  fp32: within
+    the per-query near-tie count of the fp64 truth, and within twice that of the oracle's own fp32 ranks."""
+    import parity_units as PU
     from oracle import chk_oracle as O
     n_ent, n_rel2, nq = 1500, 12, 210
     p = _random_params(name, rank, n_ent, n_rel2, dtype, True, seed=7 * rank)
     model = _model_from_params(p, name)
+    model.rank_algo = algo
     rng = np.random.default_rng(rank)
     pop = 1.0 / np.arange(1, n_ent + 1)
     pop /= pop.sum()
@@ -224,7 +273,13 @@ def test_ranking_vs_oracle(name, rank, dtype):
     if dtype == torch.float64:
         assert d.max() == 0, d.max()
     else:
-        assert d.max() <= 3 and (d > 0).mean() < 0.05, (d.max(), (d > 0).mean())
+        truth, near = PU.rank_band_counts(p, ex, filters, K_BAND)
+        d_truth = np.abs(got - truth.numpy())
+        assert (d_truth <= near.numpy()).all(), (d_truth.max(), near.max().item())
+        assert (d <= 2 * near.numpy()).all(), (d.max(), near.max().item())
+        record_parity(f"rank_oracle_fp32/{algo}/{name}-r{rank}", max_abs_rank_diff_vs_fp32_oracle=d.max(), frac_queries_differing=(d > 0).mean(),
+                      max_abs_rank_diff_vs_fp64_truth=d_truth.max(), frac_differing_vs_fp64_truth=(d_truth > 0).mean(),
+                      mean_near_tie_count=near.float().mean().item())
 
 
 def test_ranking_shard_sum_equals_single(monkeypatch):
