@@ -68,7 +68,8 @@ __device__ __forceinline__ void group_sum3(T& a, T& b, T& c) {
 // -logsigmoid(+s) (column 0) / -logsigmoid(-s) (columns >= 1) of KGOptimizer.neg_sampling_loss (reference
 // optimizers/kg_optimizer.py:115-122), their derivative and the adjoint, with every tail row gathered ONCE.
 template <typename T, int LOGL, int P, int MODE>
-__global__ void __launch_bounds__(kWarps * 32) score_gather_kernel(SArgs<T> A) {
+__global__ void __launch_bounds__(kWarps * 32, (sizeof(T) == 4 && P <= 5) ? 4 : 1) score_gather_kernel(SArgs<T> A) {   // fp32, rank <= 129: 64 registers, so a
+    // 500-row batch (4 CTAs x 148 SMs = 592 slots) is ONE wave instead of 1.13 (ncu r2: 80 registers, 3 CTAs per SM, a second wave of 56 CTAs)
     constexpr bool BWD = MODE >= 1, TRAIN = MODE == 2;
     constexpr int L = 1 << LOGL, G = 32 / L;          // lanes per pair, pairs per warp
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

@@ -69,14 +69,17 @@ __global__ void __launch_bounds__(256) train_prep_kernel(PrepArgs A) {
 }
 
 // ---------------------------------------------------------------------------------------------------- grouping
-// work (int32): [0] nseg  [1] cursor  [2..3] pad | count[n_keys] | base[n_keys] | pos[total] | order[total] | seg[total]
+// work (int32): [0] short segments  [1] cursor  [2] long segments  [3] pad | count[n_keys] | base[n_keys] | pos[total] | order[total] |
+//               seg[total] (short-segment rows from the front, long-segment rows from the back) | slen[total] | sbase[total]
+//               (length and start in `order` of the segment listed at the same position of seg)
 struct GroupView {
-    int* hdr; int* count; int* base; int* pos; int* order; int* seg;
+    int* hdr; int* count; int* base; int* pos; int* order; int* seg; int* slen; int* sbase;
 };
 __host__ __device__ inline GroupView group_view(void* work, int64_t n_keys, int64_t total) {
     int* w = (int*)work;
     GroupView v;
     v.hdr = w; v.count = w + 4; v.base = v.count + n_keys; v.pos = v.base + n_keys; v.order = v.pos + total; v.seg = v.order + total;
+    v.slen = v.seg + total; v.sbase = v.slen + total;
     return v;
 }
 
@@ -84,22 +87,53 @@ __global__ void __launch_bounds__(256) group_count_kernel(const int64_t* __restr
     for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x)
         v.pos[g] = atomicAdd(v.count + ids[g], 1);
 }
+// The slot that arrived first at a row (pos == 0) allocates the row's segment in `order` and appends the row to the list of
+// short segments (<= SHORT_MAX slots: one warp reduces them from registers) or, from the end of the same array, to the list of
+// long segments (a whole CTA each).  The two global counters are bumped once per warp (ballot + prefix sum), not per leader.
+constexpr int SHORT_MAX = 32;
 __global__ void __launch_bounds__(256) group_alloc_kernel(const int64_t* __restrict__ ids, int64_t total, GroupView v) {
-    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
-        if (v.pos[g] != 0) continue;                                  // the slot that arrived first allocates its row's segment
-        const int id = (int)ids[g];
-        v.base[id] = atomicAdd(v.hdr + 1, v.count[id]);
-        v.seg[atomicAdd(v.hdr, 1)] = id;
+    const int lane = threadIdx.x & 31;
+    const int64_t span = (total + 31) & ~int64_t(31);
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < span; g += (int64_t)gridDim.x * blockDim.x) {
+        const bool lead = g < total && v.pos[g] == 0;
+        int id = 0, cnt = 0;
+        if (lead) { id = (int)ids[g]; cnt = v.count[id]; }
+        const bool is_long = lead && cnt > SHORT_MAX;
+        const unsigned m_lead = __ballot_sync(CHK_FULL, lead), m_long = __ballot_sync(CHK_FULL, is_long);
+        if (m_lead == 0) continue;
+        int pre = cnt;                                                   // inclusive prefix sum of the leaders' counts
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(CHK_FULL, pre, o); if (lane >= o) pre += t; }
+        const int warp_total = __shfl_sync(CHK_FULL, pre, 31);
+        const unsigned m_short = m_lead & ~m_long;
+        int base0 = 0, s0 = 0, l0 = 0;
+        if (lane == 0) {
+            base0 = atomicAdd(v.hdr + 1, warp_total);
+            if (m_short) s0 = atomicAdd(v.hdr, __popc(m_short));
+            if (m_long) l0 = atomicAdd(v.hdr + 2, __popc(m_long));
+        }
+        base0 = __shfl_sync(CHK_FULL, base0, 0); s0 = __shfl_sync(CHK_FULL, s0, 0); l0 = __shfl_sync(CHK_FULL, l0, 0);
+        if (lead) {
+            const int b0 = base0 + pre - cnt;
+            v.base[id] = b0;
+            const unsigned below = (1u << lane) - 1u;
+            const int at = is_long ? (int)total - 1 - (l0 + __popc(m_long & below)) : s0 + __popc(m_short & below);
+            v.seg[at] = id; v.slen[at] = cnt; v.sbase[at] = b0;
+        }
     }
 }
 __global__ void __launch_bounds__(256) group_order_kernel(const int64_t* __restrict__ ids, int64_t total, GroupView v) {
-    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x)
-        v.order[v.base[ids[g]] + v.pos[g]] = (int)g;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t id = ids[g];
+        const int p = v.pos[g];
+        v.order[v.base[id] + p] = (int)g;
+        if (p == 0) v.count[id] = 0;             // nobody reads the count any more (the segment list carries the lengths): ready for the next step
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------- reduce + apply
 constexpr int RWARPS = 8;                 // warps per CTA
-constexpr int SORT_CAP = 2048;            // slots of one segment a warp can sort in shared memory
+constexpr int SORT_CAP = 4096;            // slots of a long segment the CTA sorts in shared memory (longer: in place, global)
 
 template <typename T> struct RCol {
     T* param; T* s0; T* dense; int width;
@@ -111,6 +145,8 @@ template <typename T> struct RGroup {
 };
 template <typename T> struct RArgsStep {
     RGroup<T> g[CHK_RED_MAX_GROUPS]; int n_groups; int opt; const double* hyper;
+    // optional end-of-step duties of the LAST block to finish (saves the chk_step_finish launch)
+    int finish; const T* loss_part; int64_t n_loss; T* loss_accum; int* step_id; int* ticket;
 };
 
 __device__ __forceinline__ int warp_bitonic_sort(int v, int lane) {          // ascending across the 32 lanes
@@ -125,21 +161,26 @@ __device__ __forceinline__ int warp_bitonic_sort(int v, int lane) {          // 
     return v;
 }
 
-// sort buf[0..n) ascending (n <= SORT_CAP, buf padded with INT_MAX up to the next power of two) by one warp
-__device__ __forceinline__ void warp_smem_sort(int* buf, int n, int lane) {
-    int np = 64; while (np < n) np <<= 1;
-    for (int i = n + lane; i < np; i += 32) buf[i] = 0x7fffffff;
-    __syncwarp();
-    for (int k = 2; k <= np; k <<= 1)
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = lane; t < (np >> 1); t += 32) {
-                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));          // index with bit j clear
-                const int a = buf[i], b = buf[i | j];
-                const bool up = (i & k) == 0;
-                if ((a > b) == up) { buf[i] = b; buf[i | j] = a; }
-            }
-            __syncwarp();
+// Ascending sort of buf[0..n) (shared or global memory) by the whole CTA: bitonic network in its ascending-only form (the
+// first step of every merge compares mirrored positions), so positions >= n act as +infinity without being stored and any
+// n works in place.
+__device__ __forceinline__ void cta_sort(int* buf, int n) {
+    int np = 2; while (np < n) np <<= 1;
+    for (int k = 2; k <= np; k <<= 1) {
+        for (int t = threadIdx.x; t < (np >> 1); t += blockDim.x) {                 // mirror step
+            const int h = k >> 1;
+            const int i = ((t / h) * k) + (t % h), l = i ^ (k - 1);
+            if (l < n) { const int a = buf[i], b = buf[l]; if (a > b) { buf[i] = b; buf[l] = a; } }
         }
+        __syncthreads();
+        for (int j = k >> 2; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < (np >> 1); t += blockDim.x) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), l = i | j;
+                if (l < n) { const int a = buf[i], b = buf[l]; if (a > b) { buf[i] = b; buf[l] = a; } }
+            }
+            __syncthreads();
+        }
+    }
 }
 
 template <typename T>
@@ -155,118 +196,178 @@ template <> struct V2<double> { using type = double2; };
 // address of the contribution row of global slot s for source i of a column (rank-major slot numbering)
 template <typename T>
 __device__ __forceinline__ const T* src_row(const RCol<T>& c, int i, int s, int spr) {
-    const int k = s / spr, ls = s - k * spr;
-    if (ls < c.lo[i] || ls >= c.hi[i]) return nullptr;
+    int k = 0, ls = s;
+    if (s >= spr) { k = s / spr; ls = s - k * spr; }
+    if (ls < c.lo[i] || ls >= c.hi[i] || !c.src[i]) return nullptr;
     return c.src[i] + (int64_t)k * c.rstride[i] + (int64_t)(ls - c.lo[i]) * c.width;
 }
 
-template <typename T>
-__global__ void __launch_bounds__(RWARPS * 32) reduce_apply_kernel(const RArgsStep<T> A) {
+// One warp sums NCH 64-element chunks (two elements per lane each), starting at chunk ch0, of one column over the slots
+// slot_at(0..len) IN THAT ORDER, then applies Adagrad to / writes the dense gradient of those elements of row `id`.
+// The parameter / state elements are loaded before the summation so their latency overlaps the contribution rows'.
+template <typename T, int NCH, typename SlotAt>
+__device__ __forceinline__ void col_chunks(const RCol<T>& c, int id, int len, int spr, int ch0, T lr, T eps, int lane, SlotAt slot_at) {
     using V = typename V2<T>::type;
-    extern __shared__ int sort_smem[];                                 // [RWARPS][SORT_CAP]
+    const int w2 = c.width >> 1;
+    const int64_t rowoff = (int64_t)id * c.width;
+    V acc[NCH], pv[NCH], av[NCH];
+    bool on[NCH];
+#pragma unroll
+    for (int h = 0; h < NCH; ++h) {
+        acc[h].x = T(0); acc[h].y = T(0);
+        on[h] = (ch0 + h) * 32 + lane < w2;
+        if (!c.dense && on[h]) {
+            pv[h] = reinterpret_cast<const V*>(c.param + rowoff)[(ch0 + h) * 32 + lane];
+            av[h] = reinterpret_cast<const V*>(c.s0 + rowoff)[(ch0 + h) * 32 + lane];
+        }
+    }
+    constexpr int U = NCH <= 2 ? 4 : 2;                             // rows in flight
+    for (int k0 = 0; k0 < len; k0 += U) {
+        V v[U][NCH];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int s = k0 + u < len ? slot_at(k0 + u) : -1;
+            const T* p = nullptr;                                       // a slot belongs to at most one source range
+            if (s >= 0) {
+                p = src_row<T>(c, 0, s, spr);
+                if (!p && c.src[1]) p = src_row<T>(c, 1, s, spr);
+            }
+#pragma unroll
+            for (int h = 0; h < NCH; ++h) {
+                v[u][h].x = T(0); v[u][h].y = T(0);
+                if (p && on[h]) v[u][h] = reinterpret_cast<const V*>(p)[(ch0 + h) * 32 + lane];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int h = 0; h < NCH; ++h) { acc[h].x += v[u][h].x; acc[h].y += v[u][h].y; }
+    }
+#pragma unroll
+    for (int h = 0; h < NCH; ++h) {
+        if (!on[h]) continue;
+        const int cc = (ch0 + h) * 32 + lane;
+        if (c.dense) reinterpret_cast<V*>(c.dense + rowoff)[cc] = acc[h];
+        else {
+            adagrad_apply<T>(pv[h].x, acc[h].x, av[h].x, lr, eps); adagrad_apply<T>(pv[h].y, acc[h].y, av[h].y, lr, eps);
+            reinterpret_cast<V*>(c.param + rowoff)[cc] = pv[h]; reinterpret_cast<V*>(c.s0 + rowoff)[cc] = av[h];
+        }
+    }
+}
+
+// scalar column (bh, bt, c): lane-strided loads in slot order, fixed butterfly (deterministic for a given slot order)
+template <typename T, typename SlotAtLane>
+__device__ __forceinline__ void col_scalar(const RCol<T>& c, int id, int len, int spr, T lr, T eps, int lane, SlotAtLane slot_of_pos) {
+    T acc = T(0);
+    for (int k0 = 0; k0 < len; k0 += 32) {
+        const int k = k0 + lane;
+        const int s = k < len ? slot_of_pos(k) : -1;
+        T v = T(0);
+        if (s >= 0) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) if (c.src[i]) { const T* p = src_row<T>(c, i, s, spr); if (p) v += *p; }
+        }
+        acc += warp_sum<T>(v);
+    }
+    if (lane == 0) {
+        if (c.dense) c.dense[id] = acc;
+        else { T p = c.param[id], a = c.s0[id]; adagrad_apply<T>(p, acc, a, lr, eps); c.param[id] = p; c.s0[id] = a; }
+    }
+}
+
+constexpr int MAXCH = 2;                  // 64-element chunks a warp accumulates per work item (keeps the kernel at <= 64 registers)
+
+template <typename T>
+__global__ void __launch_bounds__(RWARPS * 32, 4) reduce_apply_kernel(const RArgsStep<T> A) {
+    __shared__ int sbuf[SORT_CAP];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int* sbuf = sort_smem + warp * SORT_CAP;
     const RGroup<T>& G = A.g[blockIdx.y];
     const T lr = (T)A.hyper[0], eps = (T)A.hyper[1];
-    const int nseg = G.single ? 1 : G.v.hdr[0];
     const int spr = G.slots_per_rank;
-    for (int sg = blockIdx.x * RWARPS + warp; sg < nseg; sg += gridDim.x * RWARPS) {
-        int id = 0, len = G.total, base = 0;
-        if (!G.single) { id = G.v.seg[sg]; len = G.v.count[id]; base = G.v.base[id]; }
-        // ---- the segment's slots in ascending order: registers (<= 32), shared memory (<= SORT_CAP), else selection
+    // ---- phase 1: short segments (<= 32 slots).  Work item = (segment, chunk group): one warp sorts the segment's slot list
+    //      in registers and reduces MAXCH 64-element chunks of every column (wide rows are split over several warps; the
+    //      scalar columns ride with chunk group 0).
+    int ncg = 1;                                                       // chunk groups per segment = widest column's
+    for (int ci = 0; ci < G.n_cols; ++ci) {
+        const int nch = ((G.col[ci].width >> 1) + 31) >> 5;
+        ncg = max(ncg, (nch + MAXCH - 1) / MAXCH);
+    }
+    const int nshort = G.single ? 0 : G.v.hdr[0];
+    const int nitems = nshort * ncg;
+    for (int it = blockIdx.x * RWARPS + warp; it < nitems; it += gridDim.x * RWARPS) {
+        const int sg = it / ncg, cg = it - sg * ncg;
+        const int id = G.v.seg[sg];
+        const int len = G.v.slen[sg], base = G.v.sbase[sg];
         int mine = 0x7fffffff;
-        const int* sorted = nullptr;                                   // non-null: sorted list in memory
-        if (G.single) {
-            sorted = nullptr;                                          // identity order, slot = position
-        } else if (len <= 32) {
-            if (lane < len) mine = G.v.order[base + lane];
-            mine = warp_bitonic_sort(mine, lane);
-        } else if (len <= SORT_CAP) {
-            for (int i = lane; i < len; i += 32) sbuf[i] = G.v.order[base + i];
-            warp_smem_sort(sbuf, len, lane);
-            sorted = sbuf;
-        } else {
-            // pathological segment (one row named by > SORT_CAP slots): in-place selection sort in global memory by the warp
-            int* o = G.v.order + base;
-            for (int k = 0; k < len - 1; ++k) {
-                int best = 0x7fffffff, at = -1;
-                for (int i = k + lane; i < len; i += 32) { const int x = o[i]; if (x < best) { best = x; at = i; } }
-#pragma unroll
-                for (int d = 16; d > 0; d >>= 1) {
-                    const int ob = __shfl_xor_sync(CHK_FULL, best, d), oa = __shfl_xor_sync(CHK_FULL, at, d);
-                    if (ob < best) { best = ob; at = oa; }
-                }
-                if (lane == 0 && at != k) { o[at] = o[k]; o[k] = best; }
-                __syncwarp();
-            }
-            sorted = o;
-        }
-        auto slot_at = [&](int k) -> int {
-            if (G.single) return k;
-            if (sorted) return sorted[k];
-            return __shfl_sync(CHK_FULL, mine, k);
-        };
-        // ---- every column of the group: sum the contribution rows in slot order, then update / write the row
+        if (lane < len) mine = G.v.order[base + lane];
+        if (len > 1) mine = warp_bitonic_sort(mine, lane);
+        auto slot_at = [&](int k) -> int { return __shfl_sync(CHK_FULL, mine, k); };
         for (int ci = 0; ci < G.n_cols; ++ci) {
             const RCol<T>& c = G.col[ci];
-            const int64_t rowoff = (int64_t)id * c.width;
-            if (c.width == 1) {
-                // scalar column: lane-strided loads in slot order, fixed butterfly (deterministic for a given sorted order)
-                T acc = T(0);
-                for (int k0 = 0; k0 < len; k0 += 32) {
-                    const int k = k0 + lane;
-                    int s = (G.single || sorted) ? (k < len ? (G.single ? k : sorted[k]) : -1) : (k < len ? mine : -1);
-                    T v = T(0);
-                    if (s >= 0) {
-#pragma unroll
-                        for (int i = 0; i < 2; ++i) if (c.src[i]) { const T* p = src_row<T>(c, i, s, spr); if (p) v += *p; }
-                    }
-                    acc += warp_sum<T>(v);
-                }
-                if (lane == 0) {
-                    if (c.dense) c.dense[rowoff] = acc;
-                    else { T p = c.param[rowoff], a = c.s0[rowoff]; adagrad_apply<T>(p, acc, a, lr, eps); c.param[rowoff] = p; c.s0[rowoff] = a; }
-                }
-                continue;
-            }
-            const int w2 = c.width >> 1;                               // even widths: two elements per lane
-            for (int c0 = 0; c0 < w2; c0 += 32) {
-                const int cc = c0 + lane;
-                const bool on = cc < w2;
-                V acc; acc.x = T(0); acc.y = T(0);
-                for (int k0 = 0; k0 < len; k0 += 4) {                  // four rows in flight, added in slot order
-                    V v[4][2];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int k = k0 + u;
-                        const int s = k < len ? slot_at(k) : -1;
-#pragma unroll
-                        for (int i = 0; i < 2; ++i) {
-                            v[u][i].x = T(0); v[u][i].y = T(0);
-                            if (s >= 0 && c.src[i] && on) {
-                                const T* p = src_row<T>(c, i, s, spr);
-                                if (p) v[u][i] = reinterpret_cast<const V*>(p)[cc];
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-#pragma unroll
-                        for (int i = 0; i < 2; ++i) { acc.x += v[u][i].x; acc.y += v[u][i].y; }
-                }
-                if (on) {
-                    if (c.dense) reinterpret_cast<V*>(c.dense + rowoff)[cc] = acc;
-                    else {
-                        V p = reinterpret_cast<V*>(c.param + rowoff)[cc], a = reinterpret_cast<V*>(c.s0 + rowoff)[cc];
-                        adagrad_apply<T>(p.x, acc.x, a.x, lr, eps); adagrad_apply<T>(p.y, acc.y, a.y, lr, eps);
-                        reinterpret_cast<V*>(c.param + rowoff)[cc] = p; reinterpret_cast<V*>(c.s0 + rowoff)[cc] = a;
-                    }
-                }
+            if (c.width == 1) { if (cg == 0) col_scalar<T>(c, id, len, spr, lr, eps, lane, [&](int) -> int { return mine; }); continue; }
+            const int nch = ((c.width >> 1) + 31) >> 5, ch = cg * MAXCH;
+            if (ch + 1 < nch) col_chunks<T, 2>(c, id, len, spr, ch, lr, eps, lane, slot_at);
+            else if (ch < nch) col_chunks<T, 1>(c, id, len, spr, ch, lr, eps, lane, slot_at);
+        }
+    }
+    // ---- phase 2: long segments (and the single-row group), one CTA each: CTA-wide sort of the slot list, then every warp
+    //      owns column chunks warp, warp + 8, ... over ALL slots in order (no cross-warp combination: deterministic)
+    const int nlong = G.single ? 1 : G.v.hdr[2];
+    for (int li = blockIdx.x; li < nlong; li += gridDim.x) {
+        int id = 0, len = G.total, base = 0;
+        const int* sorted = nullptr;                                   // nullptr: identity order (single-row group)
+        __syncthreads();                                               // sbuf of the previous segment is free
+        if (!G.single) {
+            id = G.v.seg[G.total - 1 - li]; len = G.v.slen[G.total - 1 - li]; base = G.v.sbase[G.total - 1 - li];
+            int* o = G.v.order + base;
+            if (len <= SORT_CAP) {
+                for (int i = threadIdx.x; i < len; i += blockDim.x) sbuf[i] = o[i];
+                __syncthreads();
+                cta_sort(sbuf, len);
+                sorted = sbuf;
+            } else {
+                __syncthreads();
+                cta_sort(o, len);                                      // pathological: > SORT_CAP slots name one row
+                sorted = o;
             }
         }
-        __syncwarp();
-        if (!G.single && lane == 0) G.v.count[id] = 0;                 // the count array is all-zero again for the next step
+        auto slot_at = [&](int k) -> int { return sorted ? sorted[k] : k; };
+        for (int ci = 0; ci < G.n_cols; ++ci) {
+            const RCol<T>& c = G.col[ci];
+            if (c.width == 1) { if (warp == 0) col_scalar<T>(c, id, len, spr, lr, eps, lane, slot_at); continue; }
+            const int nch = ((c.width >> 1) + 31) >> 5;
+            for (int ch = warp; ch < nch; ch += RWARPS) col_chunks<T, 1>(c, id, len, spr, ch, lr, eps, lane, slot_at);
+        }
     }
+    if (!A.finish) return;
+    // ---- end of step: the block that finishes last resets the grouping headers, adds the loss partials in a fixed order
+    //      and bumps the step counter (every other block is past its last read of them)
+    __shared__ int last_flag;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last_flag = atomicAdd(A.ticket, 1) == (int)(gridDim.x * gridDim.y) - 1;
+    __syncthreads();
+    if (!last_flag) return;
+    if (threadIdx.x < A.n_groups && !A.g[threadIdx.x].single) {
+        int* h = A.g[threadIdx.x].v.hdr;
+        h[0] = 0; h[1] = 0; h[2] = 0;
+    }
+    if (threadIdx.x == 0) *A.ticket = 0;
+    if (A.loss_part) {
+        T acc = T(0);
+        for (int64_t i = threadIdx.x; i < A.n_loss; i += blockDim.x) acc += A.loss_part[i];
+        acc = warp_sum<T>(acc);
+        T* red = reinterpret_cast<T*>(sbuf);
+        __syncthreads();
+        if (lane == 0) red[warp] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            T t = T(0);
+            for (int w = 0; w < RWARPS; ++w) t += red[w];
+            *A.loss_accum += t;
+        }
+    }
+    if (threadIdx.x == 0 && A.step_id) *A.step_id += 1;
 }
 
 // reset the grouping headers (nseg, cursor) after the reduce of a step
@@ -275,7 +376,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) step_finish_kernel(HdrList H, const T* __restrict__ loss_part, int64_t n_loss, T* __restrict__ loss_accum,
                                                           int* __restrict__ step_id) {
     __shared__ T red[8];
-    if (threadIdx.x < H.n) { H.h[threadIdx.x][0] = 0; H.h[threadIdx.x][1] = 0; }
+    if (threadIdx.x < H.n) { H.h[threadIdx.x][0] = 0; H.h[threadIdx.x][1] = 0; H.h[threadIdx.x][2] = 0; }
     if (loss_part) {                                                   // fixed-order sum of the per-row loss partials
         T acc = T(0);
         for (int64_t i = threadIdx.x; i < n_loss; i += blockDim.x) acc += loss_part[i];
@@ -393,7 +494,7 @@ extern "C" int chk_train_prep(const int64_t* batch, int64_t B, int64_t neg, int6
 
 extern "C" int64_t chk_group_workspace_bytes(int64_t n_keys, int64_t total_slots) {
     if (n_keys < 1 || total_slots < 0 || n_keys > 0x7fffffff || total_slots > 0x7fffffff) return -1;
-    return (int64_t)sizeof(int) * (4 + 2 * n_keys + 3 * total_slots);
+    return (int64_t)sizeof(int) * (4 + 2 * n_keys + 5 * total_slots);
 }
 
 extern "C" int chk_group_build(const int64_t* ids, int64_t total_slots, int64_t n_keys, void* work, void* stream) {
@@ -410,9 +511,15 @@ extern "C" int chk_group_build(const int64_t* ids, int64_t total_slots, int64_t 
 }
 
 template <typename T>
-static int reduce_apply_t(int opt, const chk_red_group* groups, int n_groups, const double* hyper, cudaStream_t st) {
+static int reduce_apply_t(int opt, const chk_red_group* groups, int n_groups, const double* hyper, int finish, const void* loss_part,
+                          int64_t n_loss, void* loss_accum, int32_t* step_id, cudaStream_t st) {
     RArgsStep<T> A{};
     A.n_groups = n_groups; A.opt = opt; A.hyper = hyper;
+    A.finish = finish; A.loss_part = (const T*)loss_part; A.n_loss = n_loss; A.loss_accum = (T*)loss_accum; A.step_id = step_id;
+    if (finish) {
+        for (int gi = 0; gi < n_groups && !A.ticket; ++gi) if (!groups[gi].single_row && groups[gi].work) A.ticket = (int*)groups[gi].work + 3;
+        if (!A.ticket || (loss_part && !loss_accum)) { chk_set_error("chk_reduce_apply: finish needs a grouped group (ticket) and loss_accum with loss_part"); return CHK_EINVAL; }
+    }
     int64_t max_seg = 1;
     for (int gi = 0; gi < n_groups; ++gi) {
         const chk_red_group& g = groups[gi];
@@ -432,25 +539,23 @@ static int reduce_apply_t(int opt, const chk_red_group* groups, int n_groups, co
             C.param = (T*)c.param; C.s0 = (T*)c.state0; C.dense = (T*)c.dense_grad; C.width = (int)c.width;
             for (int i = 0; i < 2; ++i) { C.src[i] = (const T*)c.src[i]; C.lo[i] = (int)c.lo[i]; C.hi[i] = (int)c.hi[i]; C.rstride[i] = c.rank_stride[i]; }
         }
-        if (!g.single_row && total > max_seg) max_seg = total;
+        if (!g.single_row) {
+            int64_t ncg = 1;
+            for (int ci = 0; ci < g.n_cols; ++ci) { const int64_t nch = ((g.cols[ci].width >> 1) + 31) >> 5; if ((nch + MAXCH - 1) / MAXCH > ncg) ncg = (nch + MAXCH - 1) / MAXCH; }
+            if (total * ncg > max_seg) max_seg = total * ncg;
+        }
     }
-    static bool attr_set = false;
-    const size_t smem = (size_t)RWARPS * SORT_CAP * sizeof(int);
-    if (!attr_set) {
-        cudaFuncSetAttribute(reduce_apply_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(reduce_apply_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_set = true;
-    }
-    dim3 grid((unsigned)grid_for(max_seg, RWARPS, 148 * 6), (unsigned)n_groups);
-    reduce_apply_kernel<T><<<grid, RWARPS * 32, smem, st>>>(A);
+    dim3 grid((unsigned)grid_for(max_seg, RWARPS, 148 * 8), (unsigned)n_groups);
+    reduce_apply_kernel<T><<<grid, RWARPS * 32, 0, st>>>(A);
     CHK_CUDA_LAUNCH_CHECK("reduce_apply_kernel");
     return CHK_OK;
 }
 
-extern "C" int chk_reduce_apply(int dtype, int opt, const chk_red_group* groups, int n_groups, const double* hyper, void* stream) {
+extern "C" int chk_reduce_apply(int dtype, int opt, const chk_red_group* groups, int n_groups, const double* hyper,
+                                int finish_step, const void* loss_part, int64_t n_loss, void* loss_accum, int32_t* step_id, void* stream) {
     if (n_groups < 1 || n_groups > CHK_RED_MAX_GROUPS || !groups || !hyper) { chk_set_error("chk_reduce_apply: bad argument"); return CHK_EINVAL; }
-    if (dtype == CHK_F32) return reduce_apply_t<float>(opt, groups, n_groups, hyper, (cudaStream_t)stream);
-    if (dtype == CHK_F64) return reduce_apply_t<double>(opt, groups, n_groups, hyper, (cudaStream_t)stream);
+    if (dtype == CHK_F32) return reduce_apply_t<float>(opt, groups, n_groups, hyper, finish_step, loss_part, n_loss, loss_accum, step_id, (cudaStream_t)stream);
+    if (dtype == CHK_F64) return reduce_apply_t<double>(opt, groups, n_groups, hyper, finish_step, loss_part, n_loss, loss_accum, step_id, (cudaStream_t)stream);
     chk_set_error("unknown dtype %d", dtype); return CHK_EINVAL;
 }
 

@@ -526,11 +526,17 @@ def _red_groups(groups):
     return arr
 
 
-def reduce_apply(dtype_of, opt, groups, hyper):
-    """Segment-reduce the contribution rows of every touched row and apply Adagrad in place / write the dense gradient."""
+def reduce_apply(dtype_of, opt, groups, hyper, finish=None):
+    """Segment-reduce the contribution rows of every touched row and apply Adagrad in place / write the dense gradient.
+    finish = (loss_part, loss_accum, step_id): the kernel's last block also ends the step (chk_step_finish's duties)."""
     _chk(hyper)
     arr = groups if not isinstance(groups, list) else _red_groups(groups)
-    _lib.check(_lib.lib().chk_reduce_apply(_dt(dtype_of), opt, arr, len(arr), _p(hyper), _stream()), "chk_reduce_apply")
+    lp = la = sid = None
+    if finish is not None:
+        lp, la, sid = finish
+        _chk(lp, la, sid)
+    _lib.check(_lib.lib().chk_reduce_apply(_dt(dtype_of), opt, arr, len(arr), _p(hyper), int(finish is not None), _p(lp),
+                                           0 if lp is None else lp.numel(), _p(la), _p(sid), _stream()), "chk_reduce_apply")
     _launched(1)
 
 

@@ -253,12 +253,15 @@ class FusedKGOptimizer(KGOptimizer):
         """Segment-reduce + optimizer."""
         m = self.model
         torch.cuda.current_stream().wait_stream(self._side)
-        ops.reduce_apply(m.entity.weight, ops.CHK_OPT_ADAGRAD if self.kind == "adagrad" else ops.CHK_OPT_NONE, pl.red, self._hyper)
-        if self.kind == "adam":
+        if self.kind == "adam":                       # Adam reads the step number after the reduce: the step ends in its own launch
+            ops.reduce_apply(m.entity.weight, ops.CHK_OPT_NONE, pl.red, self._hyper)
             st = self.optimizer.state
             ops.dense_apply(ops.CHK_OPT_ADAM, [(p.data, p.grad, st[p]["exp_avg"], st[p]["exp_avg_sq"]) for p in m.parameters()],
                             self._hyper, self._step_id)
-        ops.step_finish(m.entity.weight, pl.works, pl.loss_part, self._loss_sum, self._step_id)
+            ops.step_finish(m.entity.weight, pl.works, pl.loss_part, self._loss_sum, self._step_id)
+        else:                                         # the reduce kernel's last block ends the step
+            ops.reduce_apply(m.entity.weight, ops.CHK_OPT_ADAGRAD if self.kind == "adagrad" else ops.CHK_OPT_NONE, pl.red, self._hyper,
+                             finish=(pl.loss_part, self._loss_sum, self._step_id))
 
     def _step_body(self, pl):
         self._forward_backward(pl)

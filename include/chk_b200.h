@@ -192,7 +192,10 @@ typedef struct chk_red_group {
     const int64_t* ids; int64_t n_keys; int64_t slots_per_rank; int32_t world; int32_t n_cols; int32_t single_row; int32_t pad_;
     void* work; chk_red_col cols[CHK_RED_MAX_COLS];
 } chk_red_group;
-int chk_reduce_apply(int dtype, int opt, const chk_red_group* groups, int n_groups, const double* hyper, void* stream);
+/* finish_step != 0: the last block of the launch also does chk_step_finish's duties (headers reset, loss partials summed
+ * in a fixed order into *loss_accum, *step_id bumped; loss_part / step_id may be NULL), saving that launch. */
+int chk_reduce_apply(int dtype, int opt, const chk_red_group* groups, int n_groups, const double* hyper,
+                     int finish_step, const void* loss_part, int64_t n_loss, void* loss_accum, int32_t* step_id, void* stream);
 /* End of a step: resets the grouping headers, adds the per-row loss partials (fixed order) to *loss_accum, bumps *step_id.
  * loss_part / step_id may be NULL. */
 int chk_step_finish(int dtype, void* const* group_works, int n_groups, const void* loss_part, int64_t n_loss, void* loss_accum,
