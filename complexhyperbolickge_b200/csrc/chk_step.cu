@@ -149,6 +149,27 @@ template <typename T> struct RArgsStep {
     int finish; const T* loss_part; int64_t n_loss; T* loss_accum; int* step_id; int* ticket;
 };
 
+template <int N>
+__device__ __forceinline__ int warp_bitonic_sort_n(int v, int lane) {        // ascending across the first N lanes (N = 2^m <= 32)
+#pragma unroll
+    for (int k = 2; k <= N; k <<= 1)
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const int o = __shfl_xor_sync(CHK_FULL, v, j);
+            const bool up = ((lane & k) == 0) == ((lane & j) == 0);
+            v = up ? min(v, o) : max(v, o);
+        }
+    return v;
+}
+// lanes >= len hold INT_MAX; only as many stages as the (warp-uniform) length needs
+__device__ __forceinline__ int warp_sort_len(int v, int lane, int len) {
+    if (len <= 1) return v;
+    if (len <= 2) return warp_bitonic_sort_n<2>(v, lane);
+    if (len <= 4) return warp_bitonic_sort_n<4>(v, lane);
+    if (len <= 8) return warp_bitonic_sort_n<8>(v, lane);
+    if (len <= 16) return warp_bitonic_sort_n<16>(v, lane);
+    return warp_bitonic_sort_n<32>(v, lane);
+}
 __device__ __forceinline__ int warp_bitonic_sort(int v, int lane) {          // ascending across the 32 lanes
 #pragma unroll
     for (int k = 2; k <= 32; k <<= 1)
@@ -277,66 +298,217 @@ __device__ __forceinline__ void col_scalar(const RCol<T>& c, int id, int len, in
 
 constexpr int MAXCH = 2;                  // 64-element chunks a warp accumulates per work item (keeps the kernel at <= 64 registers)
 
+// Short-segment column pass with LANE-PARALLEL row addressing: lane k holds the address of the contribution row of the k-th
+// slot (rp, nullptr when the slot does not feed this column), so a row costs two shuffles + NCH loads + the adds instead of
+// re-deriving its address per chunk.  Sums chunks ch0 .. ch0+NCH-1 (64 elements each) over k = 0..len-1 in that order.
 template <typename T>
-__global__ void __launch_bounds__(RWARPS * 32, 4) reduce_apply_kernel(const RArgsStep<T> A) {
-    __shared__ int sbuf[SORT_CAP];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const RGroup<T>& G = A.g[blockIdx.y];
-    const T lr = (T)A.hyper[0], eps = (T)A.hyper[1];
-    const int spr = G.slots_per_rank;
-    // ---- phase 1: short segments (<= 32 slots).  Work item = (segment, chunk group): one warp sorts the segment's slot list
-    //      in registers and reduces MAXCH 64-element chunks of every column (wide rows are split over several warps; the
-    //      scalar columns ride with chunk group 0).
-    int ncg = 1;                                                       // chunk groups per segment = widest column's
-    for (int ci = 0; ci < G.n_cols; ++ci) {
-        const int nch = ((G.col[ci].width >> 1) + 31) >> 5;
-        ncg = max(ncg, (nch + MAXCH - 1) / MAXCH);
-    }
-    const int nshort = G.single ? 0 : G.v.hdr[0];
-    const int nitems = nshort * ncg;
-    for (int it = blockIdx.x * RWARPS + warp; it < nitems; it += gridDim.x * RWARPS) {
-        const int sg = it / ncg, cg = it - sg * ncg;
-        const int id = G.v.seg[sg];
-        const int len = G.v.slen[sg], base = G.v.sbase[sg];
-        int mine = 0x7fffffff;
-        if (lane < len) mine = G.v.order[base + lane];
-        if (len > 1) mine = warp_bitonic_sort(mine, lane);
-        auto slot_at = [&](int k) -> int { return __shfl_sync(CHK_FULL, mine, k); };
-        for (int ci = 0; ci < G.n_cols; ++ci) {
-            const RCol<T>& c = G.col[ci];
-            if (c.width == 1) { if (cg == 0) col_scalar<T>(c, id, len, spr, lr, eps, lane, [&](int) -> int { return mine; }); continue; }
-            const int nch = ((c.width >> 1) + 31) >> 5, ch = cg * MAXCH;
-            if (ch + 1 < nch) col_chunks<T, 2>(c, id, len, spr, ch, lr, eps, lane, slot_at);
-            else if (ch < nch) col_chunks<T, 1>(c, id, len, spr, ch, lr, eps, lane, slot_at);
+__device__ __forceinline__ const T* shfl_ptr(const T* p, int k) {
+    const unsigned long long v = (unsigned long long)p;
+    const unsigned lo = __shfl_sync(CHK_FULL, (unsigned)v, k), hi = __shfl_sync(CHK_FULL, (unsigned)(v >> 32), k);
+    return (const T*)(((unsigned long long)hi << 32) | lo);
+}
+template <typename T, int NCH>
+__device__ __forceinline__ void col_chunks_ptr(const RCol<T>& c, int id, int len, int ch0, T lr, T eps, int lane, const T* rp) {
+    using V = typename V2<T>::type;
+    const int w2 = c.width >> 1;
+    const int64_t rowoff = (int64_t)id * c.width;
+    V acc[NCH], pv[NCH], av[NCH];
+    bool on[NCH];
+#pragma unroll
+    for (int h = 0; h < NCH; ++h) {
+        acc[h].x = T(0); acc[h].y = T(0);
+        on[h] = (ch0 + h) * 32 + lane < w2;
+        if (!c.dense && on[h]) {
+            pv[h] = reinterpret_cast<const V*>(c.param + rowoff)[(ch0 + h) * 32 + lane];
+            av[h] = reinterpret_cast<const V*>(c.s0 + rowoff)[(ch0 + h) * 32 + lane];
         }
     }
-    // ---- phase 2: long segments (and the single-row group), one CTA each: CTA-wide sort of the slot list, then every warp
-    //      owns column chunks warp, warp + 8, ... over ALL slots in order (no cross-warp combination: deterministic)
-    const int nlong = G.single ? 1 : G.v.hdr[2];
-    for (int li = blockIdx.x; li < nlong; li += gridDim.x) {
-        int id = 0, len = G.total, base = 0;
-        const int* sorted = nullptr;                                   // nullptr: identity order (single-row group)
-        __syncthreads();                                               // sbuf of the previous segment is free
-        if (!G.single) {
-            id = G.v.seg[G.total - 1 - li]; len = G.v.slen[G.total - 1 - li]; base = G.v.sbase[G.total - 1 - li];
-            int* o = G.v.order + base;
-            if (len <= SORT_CAP) {
-                for (int i = threadIdx.x; i < len; i += blockDim.x) sbuf[i] = o[i];
-                __syncthreads();
-                cta_sort(sbuf, len);
-                sorted = sbuf;
-            } else {
-                __syncthreads();
-                cta_sort(o, len);                                      // pathological: > SORT_CAP slots name one row
-                sorted = o;
+    const int col0 = ch0 * 32 + lane;
+    int k = 0;
+    for (; k + 4 <= len; k += 4) {                                      // four rows in flight, added in slot order
+        V v[4][NCH];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const V* p = reinterpret_cast<const V*>(shfl_ptr<T>(rp, k + u));
+#pragma unroll
+            for (int h = 0; h < NCH; ++h) { v[u][h].x = T(0); v[u][h].y = T(0); if (p && on[h]) v[u][h] = p[col0 + h * 32]; }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int h = 0; h < NCH; ++h) { acc[h].x += v[u][h].x; acc[h].y += v[u][h].y; }
+    }
+    for (; k < len; ++k) {
+        const V* p = reinterpret_cast<const V*>(shfl_ptr<T>(rp, k));
+#pragma unroll
+        for (int h = 0; h < NCH; ++h) if (p && on[h]) { const V v = p[col0 + h * 32]; acc[h].x += v.x; acc[h].y += v.y; }
+    }
+#pragma unroll
+    for (int h = 0; h < NCH; ++h) {
+        if (!on[h]) continue;
+        const int cc = col0 + h * 32;
+        if (c.dense) reinterpret_cast<V*>(c.dense + rowoff)[cc] = acc[h];
+        else {
+            adagrad_apply<T>(pv[h].x, acc[h].x, av[h].x, lr, eps); adagrad_apply<T>(pv[h].y, acc[h].y, av[h].y, lr, eps);
+            reinterpret_cast<V*>(c.param + rowoff)[cc] = pv[h]; reinterpret_cast<V*>(c.s0 + rowoff)[cc] = av[h];
+        }
+    }
+}
+
+// partial sum of ONE 64-element chunk of a column over the slots slot_at(k), k in [k_lo, k_hi), in that order
+template <typename T, typename SlotAt>
+__device__ __forceinline__ typename V2<T>::type chunk_partial(const RCol<T>& c, int spr, int ch, int k_lo, int k_hi, int lane, SlotAt slot_at) {
+    using V = typename V2<T>::type;
+    const bool on = ch * 32 + lane < (c.width >> 1);
+    V acc; acc.x = T(0); acc.y = T(0);
+    constexpr int U = 8;
+    for (int k0 = k_lo; k0 < k_hi; k0 += U) {
+        V v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            v[u].x = T(0); v[u].y = T(0);
+            if (k0 + u < k_hi) {
+                const int s = slot_at(k0 + u);
+                const T* p = src_row<T>(c, 0, s, spr);
+                if (!p && c.src[1]) p = src_row<T>(c, 1, s, spr);
+                if (p && on) v[u] = reinterpret_cast<const V*>(p)[ch * 32 + lane];
             }
         }
-        auto slot_at = [&](int k) -> int { return sorted ? sorted[k] : k; };
+#pragma unroll
+        for (int u = 0; u < U; ++u) { acc.x += v[u].x; acc.y += v[u].y; }
+    }
+    return acc;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(RWARPS * 32, 4) reduce_apply_kernel(const RArgsStep<T> A) {
+    using V = typename V2<T>::type;
+    __shared__ int sbuf[SORT_CAP];
+    __shared__ V part[RWARPS][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const T lr = (T)A.hyper[0], eps = (T)A.hyper[1];
+    const int gwarp = blockIdx.x * RWARPS + warp, nwarps = gridDim.x * RWARPS;
+    for (int gi = 0; gi < A.n_groups; ++gi) {
+        const RGroup<T>& G = A.g[gi];
+        const int spr = G.slots_per_rank;
+        // ---- phase 1: short segments (<= 32 slots).  Work item = (segment, chunk group): one warp sorts the segment's slot
+        //      list in registers and reduces MAXCH 64-element chunks of every column (wide rows are split over several warps;
+        //      the scalar columns ride with chunk group 0).  The item's metadata (row id, length, start, slot list) is loaded
+        //      one and two items ahead, so the only exposed latency per item is the one of the rows themselves.
+        int ncg = 1;                                                   // chunk groups per segment = widest column's
         for (int ci = 0; ci < G.n_cols; ++ci) {
-            const RCol<T>& c = G.col[ci];
-            if (c.width == 1) { if (warp == 0) col_scalar<T>(c, id, len, spr, lr, eps, lane, slot_at); continue; }
-            const int nch = ((c.width >> 1) + 31) >> 5;
-            for (int ch = warp; ch < nch; ch += RWARPS) col_chunks<T, 1>(c, id, len, spr, ch, lr, eps, lane, slot_at);
+            const int nch = ((G.col[ci].width >> 1) + 31) >> 5;
+            ncg = max(ncg, (nch + MAXCH - 1) / MAXCH);
+        }
+        const int nshort = G.single ? 0 : G.v.hdr[0];
+        const int nitems = nshort * ncg;
+        auto meta = [&](int it, int& id, int& len, int& base) {
+            id = 0; len = 0; base = 0;
+            if (it < nitems) { const int sg = it / ncg; id = G.v.seg[sg]; len = G.v.slen[sg]; base = G.v.sbase[sg]; }
+        };
+        int id0, len0, base0, id1, len1, base1, mine0 = 0x7fffffff, mine1 = 0x7fffffff;
+        meta(gwarp, id0, len0, base0);
+        meta(gwarp + nwarps, id1, len1, base1);
+        if (lane < len0) mine0 = G.v.order[base0 + lane];
+        for (int it = gwarp; it < nitems; it += nwarps) {
+            int id2, len2, base2;
+            meta(it + 2 * nwarps, id2, len2, base2);                   // two ahead: metadata
+            mine1 = 0x7fffffff;
+            if (lane < len1) mine1 = G.v.order[base1 + lane];          // one ahead: its slot list
+            const int cg = it % ncg, id = id0, len = len0;
+            const int mine = warp_sort_len(mine0, lane, len);          // lane k: the k-th smallest slot of the segment
+            // scalar columns first (chunk group 0): their parameter / state loads are issued before the row traffic
+            T sp[CHK_RED_MAX_COLS], sa[CHK_RED_MAX_COLS], sv[CHK_RED_MAX_COLS];
+            if (cg == 0) {
+#pragma unroll
+                for (int ci = 0; ci < CHK_RED_MAX_COLS; ++ci) {
+                    sp[ci] = T(0); sa[ci] = T(0); sv[ci] = T(0);
+                    if (ci < G.n_cols && G.col[ci].width == 1) {
+                        const RCol<T>& c = G.col[ci];
+                        if (lane == 0 && !c.dense) { sp[ci] = c.param[id]; sa[ci] = c.s0[id]; }
+                        if (lane < len) {
+                            const T* p = src_row<T>(c, 0, mine, spr);
+                            if (!p && c.src[1]) p = src_row<T>(c, 1, mine, spr);
+                            if (p) sv[ci] = *p;
+                        }
+                    }
+                }
+            }
+            for (int ci = 0; ci < G.n_cols; ++ci) {
+                const RCol<T>& c = G.col[ci];
+                if (c.width == 1) continue;
+                const int nch = ((c.width >> 1) + 31) >> 5, ch = cg * MAXCH;
+                if (ch >= nch) continue;
+                const T* rp = nullptr;                                 // lane k: row of the k-th slot in this column's sources
+                if (lane < len) { rp = src_row<T>(c, 0, mine, spr); if (!rp && c.src[1]) rp = src_row<T>(c, 1, mine, spr); }
+                if (ch + 1 < nch) col_chunks_ptr<T, 2>(c, id, len, ch, lr, eps, lane, rp);
+                else col_chunks_ptr<T, 1>(c, id, len, ch, lr, eps, lane, rp);
+            }
+            if (cg == 0) {
+#pragma unroll
+                for (int ci = 0; ci < CHK_RED_MAX_COLS; ++ci) {
+                    if (ci < G.n_cols && G.col[ci].width == 1) {
+                        const RCol<T>& c = G.col[ci];
+                        const T g = warp_sum<T>(sv[ci]);               // fixed butterfly over the sorted positions: deterministic
+                        if (lane == 0) {
+                            if (c.dense) c.dense[id] = g;
+                            else { T pp = sp[ci], aa = sa[ci]; adagrad_apply<T>(pp, g, aa, lr, eps); c.param[id] = pp; c.s0[id] = aa; }
+                        }
+                    }
+                }
+            }
+            id0 = id1; len0 = len1; base0 = base1; mine0 = mine1;
+            id1 = id2; len1 = len2; base1 = base2;
+        }
+        // ---- phase 2: long segments (and the single-row group), one CTA each: CTA-wide sort of the slot list; per 64-element
+        //      chunk every warp sums a contiguous eighth of the slots and warp 0 adds the eight partials in warp order
+        //      (fixed order: deterministic) and applies the update
+        const int nlong = G.single ? 1 : G.v.hdr[2];
+        for (int li = blockIdx.x; li < nlong; li += gridDim.x) {
+            int id = 0, len = G.total, base = 0;
+            const int* sorted = nullptr;                               // nullptr: identity order (single-row group)
+            __syncthreads();                                           // sbuf / part of the previous segment are free
+            if (!G.single) {
+                const int at = G.total - 1 - li;
+                id = G.v.seg[at]; len = G.v.slen[at]; base = G.v.sbase[at];
+                int* o = G.v.order + base;
+                if (len <= SORT_CAP) {
+                    for (int i = threadIdx.x; i < len; i += blockDim.x) sbuf[i] = o[i];
+                    __syncthreads();
+                    cta_sort(sbuf, len);
+                    sorted = sbuf;
+                } else {
+                    __syncthreads();
+                    cta_sort(o, len);                                  // pathological: > SORT_CAP slots name one row
+                    sorted = o;
+                }
+            }
+            auto slot_at = [&](int k) -> int { return sorted ? sorted[k] : k; };
+            const int per = (len + RWARPS - 1) / RWARPS;
+            const int k_lo = min(warp * per, len), k_hi = min(k_lo + per, len);
+            for (int ci = 0; ci < G.n_cols; ++ci) {
+                const RCol<T>& c = G.col[ci];
+                if (c.width == 1) { if (warp == 0) col_scalar<T>(c, id, len, spr, lr, eps, lane, slot_at); continue; }
+                const int w2 = c.width >> 1, nch = (w2 + 31) >> 5;
+                const int64_t rowoff = (int64_t)id * c.width;
+                for (int ch = 0; ch < nch; ++ch) {
+                    part[warp][lane] = chunk_partial<T>(c, spr, ch, k_lo, k_hi, lane, slot_at);
+                    __syncthreads();
+                    if (warp == 0 && ch * 32 + lane < w2) {
+                        V acc = part[0][lane];
+#pragma unroll
+                        for (int w = 1; w < RWARPS; ++w) { acc.x += part[w][lane].x; acc.y += part[w][lane].y; }
+                        const int cc = ch * 32 + lane;
+                        if (c.dense) reinterpret_cast<V*>(c.dense + rowoff)[cc] = acc;
+                        else {
+                            V pv = reinterpret_cast<V*>(c.param + rowoff)[cc], av = reinterpret_cast<V*>(c.s0 + rowoff)[cc];
+                            adagrad_apply<T>(pv.x, acc.x, av.x, lr, eps); adagrad_apply<T>(pv.y, acc.y, av.y, lr, eps);
+                            reinterpret_cast<V*>(c.param + rowoff)[cc] = pv; reinterpret_cast<V*>(c.s0 + rowoff)[cc] = av;
+                        }
+                    }
+                    __syncthreads();
+                }
+            }
         }
     }
     if (!A.finish) return;
@@ -345,7 +517,7 @@ __global__ void __launch_bounds__(RWARPS * 32, 4) reduce_apply_kernel(const RArg
     __shared__ int last_flag;
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) last_flag = atomicAdd(A.ticket, 1) == (int)(gridDim.x * gridDim.y) - 1;
+    if (threadIdx.x == 0) last_flag = atomicAdd(A.ticket, 1) == (int)gridDim.x - 1;
     __syncthreads();
     if (!last_flag) return;
     if (threadIdx.x < A.n_groups && !A.g[threadIdx.x].single) {
@@ -545,8 +717,8 @@ static int reduce_apply_t(int opt, const chk_red_group* groups, int n_groups, co
             if (total * ncg > max_seg) max_seg = total * ncg;
         }
     }
-    dim3 grid((unsigned)grid_for(max_seg, RWARPS, 148 * 8), (unsigned)n_groups);
-    reduce_apply_kernel<T><<<grid, RWARPS * 32, 0, st>>>(A);
+    // one resident wave (4 CTAs per SM at 64 registers); every CTA walks all groups
+    reduce_apply_kernel<T><<<grid_for(max_seg, RWARPS, 148 * 4), RWARPS * 32, 0, st>>>(A);
     CHK_CUDA_LAUNCH_CHECK("reduce_apply_kernel");
     return CHK_OK;
 }
