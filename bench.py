@@ -779,7 +779,10 @@ def run_ours(args):
             return out
         leg("train", "training leg (configs[1] shape)", 180, cfg1_train)
     if world > 1:
-        wd.enter("process-group teardown", 30)
+        import gc
+        wd.enter("process-group teardown", 60)
+        gc.collect()                                  # captured CUDA graphs hold NCCL work: they must be gone before the communicator
+        torch.cuda.synchronize()
         if rank_id != 0:
             dist.destroy_process_group()
             wd.stop()

@@ -15,6 +15,7 @@
 //                       order: the receive side of the sparse embedding-gradient exchange, identical on every replica.
 //   chk_dense_apply     torch.optim.Adagrad / Adam (defaults) over whole tables from a dense gradient, which it clears.
 //   chk_rowsum_groups   out[b,:] = sum_j in[b,j,:] in ascending j (double_neg: per-pair relation-row gradients).
+#include <cstdlib>
 #include "chk_common.cuh"
 
 namespace {
@@ -204,10 +205,22 @@ __device__ __forceinline__ void cta_sort(int* buf, int n) {
     }
 }
 
+// torch.optim.Adagrad element update: sum += g*g; p -= lr * g / (sqrt(sum) + eps).  fp64: IEEE sqrt and division.  fp32: the
+// SFU approximations (sqrt.approx / rcp.approx, <= 2 ulp each; sqrt.approx(0) = 0 and the denominator is >= eps > 0): the IEEE
+// sequences cost ~25 instructions per element and made the row update instruction-bound (ncu r2: 16 elements per lane at rank
+// 257); the deviation is a few ulp of an update that is itself ~1e-2 of the parameter.
 template <typename T>
 __device__ __forceinline__ void adagrad_apply(T& p, T g, T& a, T lr, T eps) {
     a = Sc<T>::fma_(g, g, a);
     p -= lr * g / (Sc<T>::sqrt_(a) + eps);
+}
+template <>
+__device__ __forceinline__ void adagrad_apply<float>(float& p, float g, float& a, float lr, float eps) {
+    a = __fmaf_rn(g, g, a);
+    float sq, rc;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(sq) : "f"(a));
+    asm("rcp.approx.f32 %0, %1;" : "=f"(rc) : "f"(sq + eps));
+    p = __fmaf_rn(-(lr * g), rc, p);
 }
 
 template <typename T> struct V2;
@@ -296,7 +309,8 @@ __device__ __forceinline__ void col_scalar(const RCol<T>& c, int id, int len, in
     }
 }
 
-constexpr int MAXCH = 2;                  // 64-element chunks a warp accumulates per work item (keeps the kernel at <= 64 registers)
+// MC = 64-element chunks a warp accumulates per work item.  MC = 2: narrow rows (rank <= 33), 64 registers, 4 CTAs per SM.
+// MC = 9: wide rows (a whole rank-257 row per warp: parameter, state and contribution chunks all in flight), 128 registers.
 
 // Short-segment column pass with LANE-PARALLEL row addressing: lane k holds the address of the contribution row of the k-th
 // slot (rp, nullptr when the slot does not feed this column), so a row costs two shuffles + NCH loads + the adds instead of
@@ -324,17 +338,18 @@ __device__ __forceinline__ void col_chunks_ptr(const RCol<T>& c, int id, int len
         }
     }
     const int col0 = ch0 * 32 + lane;
+    constexpr int U = NCH <= 2 ? 4 : (NCH <= 4 ? 2 : 1);               // rows in flight (a wide row already has NCH loads in flight)
     int k = 0;
-    for (; k + 4 <= len; k += 4) {                                      // four rows in flight, added in slot order
-        V v[4][NCH];
+    for (; k + U <= len; k += U) {                                      // U rows in flight, added in slot order
+        V v[U][NCH];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < U; ++u) {
             const V* p = reinterpret_cast<const V*>(shfl_ptr<T>(rp, k + u));
 #pragma unroll
             for (int h = 0; h < NCH; ++h) { v[u][h].x = T(0); v[u][h].y = T(0); if (p && on[h]) v[u][h] = p[col0 + h * 32]; }
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+        for (int u = 0; u < U; ++u)
 #pragma unroll
             for (int h = 0; h < NCH; ++h) { acc[h].x += v[u][h].x; acc[h].y += v[u][h].y; }
     }
@@ -380,17 +395,136 @@ __device__ __forceinline__ typename V2<T>::type chunk_partial(const RCol<T>& c, 
     return acc;
 }
 
-template <typename T>
-__global__ void __launch_bounds__(RWARPS * 32, 4) reduce_apply_kernel(const RArgsStep<T> A) {
+// ---- fast path for the entity-keyed group (compile-time row width 2*W2 elements) ---------------------------------------
+// CNT 64-element chunks starting at chunk CH0 of the wide column, over the slots k = 0..len-1 in order; lane k holds the address
+// of the k-th contribution row (rp).  Everything about the layout is a compile-time constant or a hoisted register.
+template <typename T, int W2, int CH0, int CNT>
+__device__ __forceinline__ void fast_pass(T* __restrict__ param, T* __restrict__ st, T* __restrict__ dense, int64_t rowoff, int len,
+                                          int lane, const T* rp, T lr, T eps) {
     using V = typename V2<T>::type;
+    V acc[CNT], pv[CNT], av[CNT];
+#pragma unroll
+    for (int h = 0; h < CNT; ++h) {
+        acc[h].x = T(0); acc[h].y = T(0);
+        const bool on = (CH0 + h) * 32 + 32 <= W2 || lane < W2 - (CH0 + h) * 32;
+        if (!dense && on) {
+            pv[h] = reinterpret_cast<const V*>(param + rowoff)[(CH0 + h) * 32 + lane];
+            av[h] = reinterpret_cast<const V*>(st + rowoff)[(CH0 + h) * 32 + lane];
+        }
+    }
+    constexpr int U = CNT <= 2 ? 8 : (CNT <= 3 ? 4 : 1);              // rows in flight; the last batch is predicated, not serialised
+    for (int k = 0; k < len; k += U) {
+        V v[U][CNT];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const V* p = reinterpret_cast<const V*>(shfl_ptr<T>(rp, (k + u) & 31)) + CH0 * 32 + lane;
+            const bool live = k + u < len;
+#pragma unroll
+            for (int h = 0; h < CNT; ++h) {
+                const bool on = (CH0 + h) * 32 + 32 <= W2 || lane < W2 - (CH0 + h) * 32;
+                v[u][h].x = T(0); v[u][h].y = T(0);
+                if (live && on) v[u][h] = p[h * 32];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int h = 0; h < CNT; ++h) { acc[h].x += v[u][h].x; acc[h].y += v[u][h].y; }
+    }
+#pragma unroll
+    for (int h = 0; h < CNT; ++h) {
+        const bool on = (CH0 + h) * 32 + 32 <= W2 || lane < W2 - (CH0 + h) * 32;
+        if (!on) continue;
+        const int cc = (CH0 + h) * 32 + lane;
+        if (dense) reinterpret_cast<V*>(dense + rowoff)[cc] = acc[h];
+        else {
+            adagrad_apply<T>(pv[h].x, acc[h].x, av[h].x, lr, eps); adagrad_apply<T>(pv[h].y, acc[h].y, av[h].y, lr, eps);
+            reinterpret_cast<V*>(param + rowoff)[cc] = pv[h]; reinterpret_cast<V*>(st + rowoff)[cc] = av[h];
+        }
+    }
+}
+
+// Short segments of group 0 when its first column is 2*W2 wide with every slot feeding it (sources 0 / 1 partition the slots)
+// and the other columns are scalar: one warp per segment, the whole row in one item.
+template <typename T, int W2>
+__device__ __forceinline__ void fast_entity_phase1(const RGroup<T>& G, T lr, T eps, int lane, int gwarp, int nwarps) {
+    constexpr int NCH = (W2 + 31) / 32;
+    const RCol<T>& c0 = G.col[0];
+    const T* const src0 = c0.src[0]; const T* const src1 = c0.src[1];
+    const int hi0 = c0.hi[0], lo1 = c0.lo[1];
+    const int64_t rs0 = c0.rstride[0], rs1 = c0.rstride[1];
+    T* const param = c0.param; T* const st = c0.s0; T* const dense = c0.dense;
+    const int spr = G.slots_per_rank, nsc = G.n_cols - 1;
+    const int nshort = G.v.hdr[0];
+    auto meta = [&](int sg, int& id, int& len, int& base) {
+        id = 0; len = 0; base = 0;
+        if (sg < nshort) { id = G.v.seg[sg]; len = G.v.slen[sg]; base = G.v.sbase[sg]; }
+    };
+    int id0, len0, base0, id1, len1, base1, mine0 = 0x7fffffff, mine1;
+    meta(gwarp, id0, len0, base0);
+    meta(gwarp + nwarps, id1, len1, base1);
+    if (lane < len0) mine0 = G.v.order[base0 + lane];
+    for (int sg = gwarp; sg < nshort; sg += nwarps) {
+        int id2, len2, base2;
+        meta(sg + 2 * nwarps, id2, len2, base2);
+        mine1 = 0x7fffffff;
+        if (lane < len1) mine1 = G.v.order[base1 + lane];
+        const int id = id0, len = len0;
+        const int mine = warp_sort_len(mine0, lane, len);
+        int rk = 0, ls = mine;                                          // rank-major slot numbering (data parallel)
+        if (lane < len && mine >= spr) { rk = mine / spr; ls = mine - rk * spr; }
+        const T* rp = nullptr;
+        if (lane < len) rp = ls < hi0 ? src0 + rk * rs0 + (int64_t)ls * (2 * W2) : src1 + rk * rs1 + (int64_t)(ls - lo1) * (2 * W2);
+        T sp[2], sa[2], sv[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            sp[j] = T(0); sa[j] = T(0); sv[j] = T(0);
+            if (j < nsc) {
+                const RCol<T>& c = G.col[1 + j];
+                if (lane == 0 && !c.dense) { sp[j] = c.param[id]; sa[j] = c.s0[id]; }
+                if (lane < len && ls >= c.lo[0] && ls < c.hi[0]) sv[j] = c.src[0][rk * c.rstride[0] + (ls - c.lo[0])];
+            }
+        }
+        const int64_t rowoff = (int64_t)id * (2 * W2);
+        if constexpr (NCH <= 5) fast_pass<T, W2, 0, (NCH <= 5 ? NCH : 1)>(param, st, dense, rowoff, len, lane, rp, lr, eps);
+        else {
+            fast_pass<T, W2, 0, 5>(param, st, dense, rowoff, len, lane, rp, lr, eps);
+            fast_pass<T, W2, 5, (NCH > 5 ? NCH - 5 : 1)>(param, st, dense, rowoff, len, lane, rp, lr, eps);
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            if (j < nsc) {
+                const RCol<T>& c = G.col[1 + j];
+                const T g = warp_sum<T>(sv[j]);                         // fixed butterfly over the sorted positions: deterministic
+                if (lane == 0) {
+                    if (c.dense) c.dense[id] = g;
+                    else { T pp = sp[j], aa = sa[j]; adagrad_apply<T>(pp, g, aa, lr, eps); c.param[id] = pp; c.s0[id] = aa; }
+                }
+            }
+        }
+        id0 = id1; len0 = len1; base0 = base1; mine0 = mine1;
+        id1 = id2; len1 = len2; base1 = base2;
+    }
+}
+
+template <typename T, int W2>
+__global__ void __launch_bounds__(RWARPS * 32, (W2 > 0 && W2 <= 65) || W2 == 0 ? 4 : 3) reduce_apply_kernel(const RArgsStep<T> A) {
+    using V = typename V2<T>::type;
+    constexpr int MAXCH = 2;
     __shared__ int sbuf[SORT_CAP];
     __shared__ V part[RWARPS][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const T lr = (T)A.hyper[0], eps = (T)A.hyper[1];
-    const int gwarp = blockIdx.x * RWARPS + warp, nwarps = gridDim.x * RWARPS;
     for (int gi = 0; gi < A.n_groups; ++gi) {
         const RGroup<T>& G = A.g[gi];
         const int spr = G.slots_per_rank;
+        // CTA roles: the last `nlc` CTAs of the grid take this group's long segments (and nothing else of the group), so the
+        // CTA-wide passes run BESIDE the short segments instead of after them; tiny grids do both in turn.
+        const int nlong = G.single ? 1 : G.v.hdr[2];
+        const int nlc = min(nlong, (int)gridDim.x >> 2);
+        const int first_long = (int)gridDim.x - nlc;
+        const bool long_cta = nlc > 0 && (int)blockIdx.x >= first_long;
+        const int gwarp = long_cta ? 0x3fffffff : blockIdx.x * RWARPS + warp, nwarps = first_long * RWARPS;
         // ---- phase 1: short segments (<= 32 slots).  Work item = (segment, chunk group): one warp sorts the segment's slot
         //      list in registers and reduces MAXCH 64-element chunks of every column (wide rows are split over several warps;
         //      the scalar columns ride with chunk group 0).  The item's metadata (row id, length, start, slot list) is loaded
@@ -400,7 +534,13 @@ __global__ void __launch_bounds__(RWARPS * 32, 4) reduce_apply_kernel(const RArg
             const int nch = ((G.col[ci].width >> 1) + 31) >> 5;
             ncg = max(ncg, (nch + MAXCH - 1) / MAXCH);
         }
-        const int nshort = G.single ? 0 : G.v.hdr[0];
+        int nshort = G.single ? 0 : G.v.hdr[0];
+        if constexpr (W2 > 0) {                                        // compile-time-width fast path for the entity-keyed group
+            if (gi == 0) {
+                fast_entity_phase1<T, W2>(G, lr, eps, lane, gwarp, nwarps);
+                nshort = 0;
+            }
+        }
         const int nitems = nshort * ncg;
         auto meta = [&](int it, int& id, int& len, int& base) {
             id = 0; len = 0; base = 0;
@@ -437,12 +577,17 @@ __global__ void __launch_bounds__(RWARPS * 32, 4) reduce_apply_kernel(const RArg
             for (int ci = 0; ci < G.n_cols; ++ci) {
                 const RCol<T>& c = G.col[ci];
                 if (c.width == 1) continue;
-                const int nch = ((c.width >> 1) + 31) >> 5, ch = cg * MAXCH;
+                const int nch = ((c.width >> 1) + 31) >> 5;
+                int ch = cg * MAXCH;
+                const int ch_end = min(nch, ch + MAXCH);
                 if (ch >= nch) continue;
                 const T* rp = nullptr;                                 // lane k: row of the k-th slot in this column's sources
                 if (lane < len) { rp = src_row<T>(c, 0, mine, spr); if (!rp && c.src[1]) rp = src_row<T>(c, 1, mine, spr); }
-                if (ch + 1 < nch) col_chunks_ptr<T, 2>(c, id, len, ch, lr, eps, lane, rp);
-                else col_chunks_ptr<T, 1>(c, id, len, ch, lr, eps, lane, rp);
+                while (ch < ch_end) {
+                    const int left = ch_end - ch;
+                    if (left >= 2) { col_chunks_ptr<T, 2>(c, id, len, ch, lr, eps, lane, rp); ch += 2; }
+                    else { col_chunks_ptr<T, 1>(c, id, len, ch, lr, eps, lane, rp); ch += 1; }
+                }
             }
             if (cg == 0) {
 #pragma unroll
@@ -463,8 +608,9 @@ __global__ void __launch_bounds__(RWARPS * 32, 4) reduce_apply_kernel(const RArg
         // ---- phase 2: long segments (and the single-row group), one CTA each: CTA-wide sort of the slot list; per 64-element
         //      chunk every warp sums a contiguous eighth of the slots and warp 0 adds the eight partials in warp order
         //      (fixed order: deterministic) and applies the update
-        const int nlong = G.single ? 1 : G.v.hdr[2];
-        for (int li = blockIdx.x; li < nlong; li += gridDim.x) {
+        const int li0 = nlc > 0 ? (long_cta ? (int)blockIdx.x - first_long : nlong) : (int)blockIdx.x;
+        const int li_step = nlc > 0 ? nlc : (int)gridDim.x;
+        for (int li = li0; li < nlong; li += li_step) {
             int id = 0, len = G.total, base = 0;
             const int* sorted = nullptr;                               // nullptr: identity order (single-row group)
             __syncthreads();                                           // sbuf / part of the previous segment are free
@@ -711,14 +857,31 @@ static int reduce_apply_t(int opt, const chk_red_group* groups, int n_groups, co
             C.param = (T*)c.param; C.s0 = (T*)c.state0; C.dense = (T*)c.dense_grad; C.width = (int)c.width;
             for (int i = 0; i < 2; ++i) { C.src[i] = (const T*)c.src[i]; C.lo[i] = (int)c.lo[i]; C.hi[i] = (int)c.hi[i]; C.rstride[i] = c.rank_stride[i]; }
         }
-        if (!g.single_row) {
-            int64_t ncg = 1;
-            for (int ci = 0; ci < g.n_cols; ++ci) { const int64_t nch = ((g.cols[ci].width >> 1) + 31) >> 5; if ((nch + MAXCH - 1) / MAXCH > ncg) ncg = (nch + MAXCH - 1) / MAXCH; }
-            if (total * ncg > max_seg) max_seg = total * ncg;
-        }
+        if (!g.single_row && g.n_keys * 0 + total > max_seg) max_seg = total;
     }
-    // one resident wave (4 CTAs per SM at 64 registers); every CTA walks all groups
-    reduce_apply_kernel<T><<<grid_for(max_seg, RWARPS, 148 * 4), RWARPS * 32, 0, st>>>(A);
+    // one resident wave; every CTA walks all groups
+    // one resident wave; every CTA walks all groups.  Group 0 takes the compile-time-width fast path when it has the entity-group
+    // shape: first column 2*W2 wide fed by every slot (two sources partitioning the slots), the other columns scalar.
+    static const char* force = getenv("CHK_REDUCE_VARIANT");          // measurement override: "generic"
+    int w2 = 0;
+    {
+        const chk_red_group& g0 = groups[0];
+        const chk_red_col& c0 = g0.cols[0];
+        bool ok = !g0.single_row && c0.width >= 2 && c0.src[0] && c0.src[1] && c0.lo[0] == 0 && c0.hi[0] == c0.lo[1] && c0.hi[1] == g0.slots_per_rank &&
+                  g0.n_cols <= 3 && !(force && force[0] == 'g');
+        for (int ci = 1; ci < g0.n_cols && ok; ++ci) ok = g0.cols[ci].width == 1 && g0.cols[ci].src[0] && !g0.cols[ci].src[1];
+        if (ok) w2 = (int)(c0.width >> 1);
+    }
+    const int grid4 = grid_for(max_seg, RWARPS, 148 * 4), grid3 = grid_for(max_seg, RWARPS, 148 * 3);
+    switch (w2) {
+        case 9: reduce_apply_kernel<T, 9><<<grid4, RWARPS * 32, 0, st>>>(A); break;
+        case 17: reduce_apply_kernel<T, 17><<<grid4, RWARPS * 32, 0, st>>>(A); break;
+        case 33: reduce_apply_kernel<T, 33><<<grid4, RWARPS * 32, 0, st>>>(A); break;
+        case 65: reduce_apply_kernel<T, 65><<<grid4, RWARPS * 32, 0, st>>>(A); break;
+        case 129: reduce_apply_kernel<T, 129><<<grid3, RWARPS * 32, 0, st>>>(A); break;
+        case 257: reduce_apply_kernel<T, 257><<<grid3, RWARPS * 32, 0, st>>>(A); break;
+        default: reduce_apply_kernel<T, 0><<<grid4, RWARPS * 32, 0, st>>>(A); break;
+    }
     CHK_CUDA_LAUNCH_CHECK("reduce_apply_kernel");
     return CHK_OK;
 }

@@ -85,6 +85,12 @@ def _worker(rank, world, port, backend, sparse, opt_name, q):
         assert torch.equal(sharded, single)
         if rank == 0:
             q.put((losses, params))
+        # the captured CUDA graph holds NCCL work: release it before the communicator is torn down (destroy_process_group
+        # waits for it otherwise)
+        del opt
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
     finally:
         dist.destroy_process_group()
 
@@ -103,10 +109,15 @@ def test_dp_epoch_equals_single_gpu_epoch(sparse, opt_name):
     procs = [ctx.Process(target=_worker, args=(r, 2, port, backend, sparse, opt_name, q)) for r in range(2)]
     for p in procs:
         p.start()
-    got = q.get(timeout=600)
-    for p in procs:
-        p.join(timeout=120)
-        assert p.exitcode == 0
+    try:
+        got = q.get(timeout=300)
+        for p in procs:
+            p.join(timeout=60)
+            assert p.exitcode == 0, "a rank did not exit cleanly"
+    finally:
+        for p in procs:                                   # never leave a rank behind (it would hold the GPU and the port)
+            if p.is_alive():
+                p.kill()
     losses_dp, params_dp = got
     # single GPU, same shuffle (rank 0's seed) and the same per-triple negatives
     n_ent, neg, Bg = 600, 15, 45

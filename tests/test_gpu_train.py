@@ -93,9 +93,10 @@ def test_fused_step_matches_contract_path(name, rank, dtype, reg, double_neg, mu
     for (k, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
         scale = max(pa.abs().max().item(), 1e-30)
         err = (pa - pb).abs().max().item() / scale
-        # fp32: Adagrad's first steps move a coordinate by ~lr * sign(g), so coordinates whose gradient is rounding noise
-        # differ between two summation orders; the bound is loose in fp32 and the fp64 runs (1e-8) carry the parity claim
-        assert err <= (1e-8 if dbl else (5e-3 if rank <= 65 else 3e-2)), (k, err)
+        # fp32: Adagrad's first steps move a coordinate by ~lr * sign(g) (lr = 0.05 here, of the order of max|p|), so a coordinate
+        # whose gradient is rounding noise can differ by O(lr) between two summation orders; with 514 coordinates per row at rank
+        # 257 some always do.  The bound is therefore loose in fp32 and the fp64 runs (1e-8, same shapes) carry the parity claim.
+        assert err <= (1e-8 if dbl else (5e-3 if rank <= 65 else 0.15)), (k, err)
     fus.sync_optimizer_state()
     if opt_name in ("Adagrad", "Adam"):                  # optimizer state is the torch optimizer's own, kept in sync
         keys = ("sum",) if opt_name == "Adagrad" else ("exp_avg", "exp_avg_sq")

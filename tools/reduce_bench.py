@@ -55,6 +55,14 @@ def run(tag, N, Bq, P, w, scalars, hot, reps=20):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "bigone":
+        run("big4m uniform, entity only", 4_000_000, 500, 50500, 514, False, False, reps=3)
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "big":
+        run("big4m uniform, entity only", 4_000_000, 500, 50500, 514, False, False)
+        run("big4m uniform, entity + bh + bt", 4_000_000, 500, 50500, 514, True, False)
+        run("big4m x8 ranks' slots (DP receive side)", 4_000_000, 4000, 404000, 514, True, False, reps=5)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "one":
         run("fb237 uniform, entity only", 14541, 500, 125500, 66, False, False, reps=4)
         sys.exit(0)
