@@ -287,22 +287,19 @@ def measure_eval(model, graph, b, K, W, device, pg, world, rank_id, local, want_
     test = graph["test"]
     reps = (b * (K + W) + len(test) - 1) // len(test)
     qall = np.concatenate([test] * reps)[: b * (K + W)]
-    steps_in = []
-    for i in range(K + W):
-        qb = qall[i * b:(i + 1) * b]
-        indptr, idx = findex.batch_csr(qb)
-        steps_in.append((torch.from_numpy(qb).to(device), torch.from_numpy(indptr).to(device),
-                         torch.from_numpy(idx).to(device), int(idx.size)))
+    steps_in = [torch.from_numpy(qall[i * b:(i + 1) * b]).to(device) for i in range(K + W)]     # resident inputs: query ids in HBM
+    findex.device_arrays(device)                                                                # the filter index lives on the device
     with torch.no_grad():
         state = ranking.eval_state(model)
         mma = state.algo == ops.CHK_RANK_MMA
         ws = ops.rank_mma_workspace(rank, b, device) if mma else None
         counts = torch.zeros(b, dtype=torch.int64, device=device)
+        target_buf = torch.zeros(b, dtype=model.entity.weight.dtype, device=device)
+        flags = torch.zeros(1, dtype=torch.int32, device=device)
+        scratch = ops.eval_scratch(rank, b, model.entity.weight.dtype, device)
 
         def step(i):
-            counts.zero_()
-            qd, ip, ix, tot = steps_in[i]
-            ranking.rank_batch(model, state, qd, ip, ix, tot, counts, ws)
+            ranking.rank_batch_fused(model, state, findex, steps_in[i], counts, target_buf, flags, scratch, ws)
             if world > 1:
                 dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=pg)
 
@@ -337,7 +334,8 @@ def measure_eval(model, graph, b, K, W, device, pg, world, rank_id, local, want_
         ranks_check = (counts + 1).float().cpu()
 
         # ---- roofline: the dominant kernel alone (rank tile contraction), CUDA events on torch's stream
-        qd, ip, ix, tot = steps_in[W]
+        qd = steps_in[W]
+        ix = torch.zeros(1, dtype=torch.int64, device=device)
         ctxw = model._ctx_weight()
         q, _ = ops.query_fwd(model.KIND, rank, bool(model.multi_c), model.entity.weight.detach(), model.rel.weight.detach(),
                              model.rel_diag.weight.detach(), None if ctxw is None else ctxw.detach(),
@@ -404,7 +402,7 @@ def measure_eval(model, graph, b, K, W, device, pg, world, rank_id, local, want_
         e2e = {"value": b * K / (e_ms * 1e-3), "unit": UNIT, "ranks_equal_resident_path": same, "h2d_bytes_per_step": io["h2d_bytes"] // io["batches"],
                "d2h_bytes_per_step": io["d2h_bytes"] // io["batches"], "ms_per_step": e_ms / K,
                "api": f"model.get_ranking(host LongTensor[{K}*{b},3], FilterIndex, batch_size={b}): one call, {K} pipelined "
-                      "batches, per batch 1 H2D copy (ids + filter CSR, pinned) and 1 D2H copy (ranks)",
+                      "batches, per batch 1 H2D copy (query ids, pinned), 1 chk_eval_batch call (filter index searched on the device) and 1 D2H copy (ranks)",
                "note": "the per-pass evaluation state (Hermitian norms, bf16 shadow: one pass over the table) is cached on the model "
                        "and was built by the warm call before the timed one; it is rebuilt only after a parameter update"}
     if rank_id != 0:

@@ -43,6 +43,17 @@ class RedGroup(ctypes.Structure):
                 ("single_row", ctypes.c_int32), ("pad_", ctypes.c_int32), ("work", _p), ("cols", RedCol * CHK_RED_MAX_COLS)]
 
 
+class EvalArgs(ctypes.Structure):
+    """chk_eval_args of include/chk_b200.h."""
+    _fields_ = [("algo", ctypes.c_int32), ("kind", ctypes.c_int32), ("dtype", ctypes.c_int32), ("rank", ctypes.c_int32),
+                ("multi_c", ctypes.c_int32), ("pad_", ctypes.c_int32), ("b", _i64), ("queries", _p),
+                ("entity", _p), ("rel", _p), ("rel_diag", _p), ("ctx", _p), ("c_table", _p), ("bh", _p), ("bt", _p),
+                ("hn_full", _p), ("n_entities", _i64), ("shard_entity", _p), ("shard_hn", _p), ("shard_bt", _p),
+                ("shard_rows", _i64), ("shard_offset", _i64), ("shadow", _p), ("workspace", _p), ("workspace_bytes", _i64),
+                ("f_keys", _p), ("f_indptr", _p), ("f_vals", _p), ("f_nkeys", _i64), ("n_rel2", _i64),
+                ("scratch", _p), ("scratch_bytes", _i64), ("counts", _p), ("target", _p), ("flags", _p)]
+
+
 class DenseTab(ctypes.Structure):
     """chk_dense_tab of include/chk_b200.h."""
     _fields_ = [("param", _p), ("grad", _p), ("state0", _p), ("state1", _p), ("n", _i64)]
@@ -87,6 +98,9 @@ SIGNATURES = {
     "chk_rank_mma_reset": (_i, [_p, _p]),
     "chk_rank_mma_status": (_i, [_p, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int), _p]),
     "chk_rank_mma_profile_events": (_i, [_p, _p]),
+    "chk_filter_lookup": (_i, [_p, _i64, _i64, _p, _i64, _p, _p, _i64, _i64, _p, _p, _p, _p, _p]),
+    "chk_eval_scratch_bytes": (_i64, [_i, _i, _i64]),
+    "chk_eval_batch": (_i, [ctypes.POINTER(EvalArgs), _p]),
     "chk_score_all_mma": (_i, [_i, _i, _i64, _p, _p, _p, _p, _p, _p, _p, _i64, _p, _p, _i64, _p, _p, _p, _p]),
 }
 

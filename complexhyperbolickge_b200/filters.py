@@ -59,6 +59,18 @@ class FilterIndex:
             self.indptr, self.vals = indptr, vals.astype(np.int64)
         self._normalised = True
 
+    def device_arrays(self, device):
+        """(keys_code, indptr, vals) as int64 tensors resident on `device` (uploaded once, lists sorted and unique): what
+        chk_filter_lookup searches, so an evaluation batch needs no host-side CSR work and no CSR upload."""
+        import torch
+        self._normalise()
+        cache = self.__dict__.setdefault("_dev", {})
+        key = str(device)
+        if key not in cache:
+            up = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int64)).to(device)
+            cache[key] = (up(self.keys_code), up(self.indptr), up(self.vals if self.vals.size else np.zeros(1, np.int64)))
+        return cache[key]
+
     def batch_csr(self, queries: np.ndarray, strict: bool = True):
         """queries int64 [b,3] -> (indptr [b+1], idx [total]) with idx_i = unique(filter[(h,r)] ∪ {t}), sorted.
 

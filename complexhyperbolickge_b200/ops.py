@@ -575,3 +575,34 @@ def reg_factors(power, weight, hyper, B, entity, rel, heads, head_stride, rels, 
                                           g_ent_stride, _p(g_rel), g_rel_stride, _p(g_tail), g_tail_stride, _p(loss_part), _stream()),
                "chk_reg_factors")
     _launched(1)
+
+
+# ------------------------------------------------------------------------------------------- evaluation batch in one call
+def eval_scratch(rank, b, dtype, device):
+    n = _lib.lib().chk_eval_scratch_bytes(CHK_F32 if dtype == torch.float32 else CHK_F64, rank, b)
+    if n <= 0:
+        raise RuntimeError("chk_eval_scratch_bytes failed")
+    return torch.empty((n,), dtype=torch.uint8, device=device)
+
+
+def eval_batch(algo, kind, rank, multi_c, queries, entity, rel, rel_diag, ctx, c_table, bh, bt, hn_full, shard_entity, shard_hn,
+               shard_bt, shard_offset, shadow, workspace, f_keys, f_indptr, f_vals, n_rel2, scratch, counts, target, flags):
+    """One batch of get_ranking: K1 -> norms -> target -> rank counts -> device filter lookup -> filter pass (chk_eval_batch)."""
+    _chk(queries, entity, rel, rel_diag, ctx, c_table, bh, bt, hn_full, shard_entity, shard_hn, shard_bt, shadow, workspace, f_keys,
+         f_indptr, f_vals, scratch, counts, target, flags)
+    a = _lib.EvalArgs()
+    a.algo, a.kind, a.dtype, a.rank, a.multi_c, a.b = algo, kind, _dt(entity), rank, int(multi_c), queries.shape[0]
+    a.queries = _p(queries)
+    a.entity, a.rel, a.rel_diag, a.ctx, a.c_table, a.bh, a.bt = _p(entity), _p(rel), _p(rel_diag), _p(ctx), _p(c_table), _p(bh), _p(bt)
+    a.hn_full, a.n_entities = _p(hn_full), entity.shape[0]
+    a.shard_entity, a.shard_hn, a.shard_bt = _p(shard_entity), _p(shard_hn), _p(shard_bt)
+    a.shard_rows, a.shard_offset = shard_entity.shape[0], shard_offset
+    a.shadow, a.workspace = _p(shadow), _p(workspace)
+    a.workspace_bytes = 0 if workspace is None else workspace.numel() * workspace.element_size()
+    a.f_keys, a.f_indptr, a.f_vals, a.f_nkeys, a.n_rel2 = _p(f_keys), _p(f_indptr), _p(f_vals), f_keys.numel(), n_rel2
+    a.scratch, a.scratch_bytes = _p(scratch), scratch.numel()
+    a.counts, a.target, a.flags = _p(counts), _p(target), _p(flags)
+    import ctypes
+    _lib.check(_lib.lib().chk_eval_batch(ctypes.byref(a), _stream()), "chk_eval_batch")
+    b = queries.shape[0]
+    _launched(6 + (4 * ((b + 1023) // 1024) if algo == CHK_RANK_MMA else (shard_entity.shape[0] + 64 * 65535 - 1) // (64 * 65535)))

@@ -36,6 +36,9 @@ class EvalState:
         self.entity = ent[self.lo:self.hi].contiguous()
         self.bt = model.bt.weight.detach().view(-1)[self.lo:self.hi].contiguous() if model.bias == "learn" else None
         self.hn = ops.row_hnorm(model.rank, self.entity) if self.hi > self.lo else ent.new_empty(0)
+        # the true tails are scored straight from the full (replicated) table: its norms, once per pass
+        self.hn_full = self.hn if self.world == 1 else ops.row_hnorm(model.rank, ent.contiguous())
+        self.bt_full = model.bt.weight.detach().view(-1) if model.bias == "learn" else None
         self.algo = ops.CHK_RANK_MMA if model.resolved_rank_algo() == "mma" else ops.CHK_RANK_FMA
         self.shadow = None
         if self.algo == ops.CHK_RANK_MMA:       # fp32 and fp64 models: bf16x3 prefilter, exact re-check in the model dtype
@@ -134,10 +137,24 @@ def _send_batch(ring: _HostRing, qb: np.ndarray, indptr: np.ndarray, idx: np.nda
     return d[:3 * b].view(b, 3), d[3 * b:4 * b + 1], d[4 * b + 1:], tot, 8 * n_words
 
 
+def rank_batch_fused(model, state: EvalState, findex: FilterIndex, queries_dev: torch.Tensor, counts: torch.Tensor,
+                     target: torch.Tensor, flags: torch.Tensor, scratch: torch.Tensor, workspace=None):
+    """One evaluation batch through chk_eval_batch: a single host call enqueues K1, the query norms, the target scores,
+    the rank counts of this rank's shard and the filter pass; the filter index is searched on the device."""
+    keys, indptr, vals = findex.device_arrays(queries_dev.device)
+    ctxw = model._ctx_weight()
+    learn = model.bias == "learn"
+    ops.eval_batch(state.algo, model.KIND, model.rank, bool(model.multi_c), queries_dev, model.entity.weight.detach(),
+                   model.rel.weight.detach(), model.rel_diag.weight.detach(), None if ctxw is None else ctxw.detach(),
+                   model.c.weight.detach(), model.bh.weight.detach().view(-1) if learn else None, state.bt_full, state.hn_full,
+                   state.entity, state.hn, state.bt, state.lo, state.shadow, workspace, keys, indptr, vals, findex.n_rel2,
+                   scratch, counts, target, flags)
+
+
 def rank_queries(model, queries: torch.Tensor, findex: FilterIndex, batch_size: int) -> torch.Tensor:
-    """Filtered ranks of all queries, float32 CPU tensor [n].  The batches form a pipeline: while the GPU counts
-    batch i the host builds the filter CSR of batch i+1 in pinned memory; every batch has one H2D copy of its
-    inputs and one asynchronous D2H copy of its ranks; the host synchronises ONCE, at the end of the pass."""
+    """Filtered ranks of all queries, float32 CPU tensor [n].  Per batch: ONE H2D copy of the query ids (pinned ring), ONE
+    host call that enqueues the whole batch (chk_eval_batch; the filter index lives on the device), [sharded: one int64
+    all_reduce], ONE asynchronous D2H copy of the batch's ranks.  The host synchronises once, at the end of the pass."""
     dev = model.entity.weight.device
     if dev.type != "cuda":
         raise RuntimeError("complexhyperbolickge_b200 models run on CUDA only (no CPU fallback)")
@@ -153,6 +170,7 @@ def rank_queries(model, queries: torch.Tensor, findex: FilterIndex, batch_size: 
     model.last_eval_io = io = {"h2d_bytes": 0, "d2h_bytes": 0, "batches": 0}
     with torch.no_grad():
         state = eval_state(model)
+        dt = model.entity.weight.dtype
         ws = None
         if state.algo == ops.CHK_RANK_MMA:
             ws = getattr(model, "_eval_ws", None)
@@ -160,22 +178,31 @@ def rank_queries(model, queries: torch.Tensor, findex: FilterIndex, batch_size: 
                 model._eval_ws = ws = ((model.rank, batch_size, dev), ops.rank_mma_workspace(model.rank, batch_size, dev))
             ws = ws[1]
             ops.rank_mma_reset(ws)
+        sc = getattr(model, "_eval_scratch", None)
+        if sc is None or sc[0] != (model.rank, batch_size, dev, dt):
+            model._eval_scratch = sc = ((model.rank, batch_size, dev, dt), ops.eval_scratch(model.rank, batch_size, dt, dev))
+        scratch = sc[1]
         nan_seen = torch.zeros((), dtype=torch.bool, device=dev)
+        flags = torch.zeros(1, dtype=torch.int32, device=dev)
 
         def one_pass(state, ws):
             for b0 in range(0, n, batch_size):
                 qb = q_np[b0:b0 + batch_size]
-                indptr, idx = findex.batch_csr(qb)
-                qd, ip, ix, tot, nbytes = _send_batch(ring, qb, indptr, idx, dev)
-                counts = torch.zeros(qb.shape[0], dtype=torch.int64, device=dev)
-                target = rank_batch(model, state, qd, ip, ix, tot, counts, ws)
+                b = qb.shape[0]
+                s, host = ring.stage(3 * b)
+                host.numpy()[:3 * b] = qb.reshape(-1)
+                qd = host[:3 * b].to(dev, non_blocking=True).view(b, 3)
+                ring.sent(s)
+                counts = torch.empty(b, dtype=torch.int64, device=dev)
+                target = torch.empty(b, dtype=dt, device=dev)
+                rank_batch_fused(model, state, findex, qd, counts, target, flags, scratch, ws)
                 if state.world > 1:                      # integer partial counts of the entity shards
                     import torch.distributed as dist
                     dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=model.process_group)
-                out_host[b0:b0 + qb.shape[0]].copy_((counts + 1).to(torch.float32), non_blocking=True)
+                out_host[b0:b0 + b].copy_((counts + 1).to(torch.float32), non_blocking=True)
                 nan_seen.logical_or_(torch.isnan(target).any())   # models/base.py:259-260, checked once after the pass
-                io["h2d_bytes"] += nbytes
-                io["d2h_bytes"] += 4 * qb.shape[0]
+                io["h2d_bytes"] += 24 * b
+                io["d2h_bytes"] += 4 * b
                 io["batches"] += 1
 
         one_pass(state, ws)
@@ -192,5 +219,9 @@ def rank_queries(model, queries: torch.Tensor, findex: FilterIndex, batch_size: 
             exact.algo, exact.shadow = ops.CHK_RANK_FMA, None
             one_pass(exact, None)
         nan_host = bool(nan_seen)                        # synchronises the stream: every D2H copy above has landed
+        missing = bool(flags.item() & 1)
+    if missing:
+        findex.batch_csr(q_np)                           # raises KeyError naming the (entity, relation) the reference would (base.py:266)
+        raise KeyError("a query key is missing from the filter index")
     assert not nan_host, "NaN score in get_ranking"
     return out_host[:n].clone()

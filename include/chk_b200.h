@@ -279,6 +279,35 @@ int chk_score_all_mma(int dtype, int rank, int64_t b, const void* q, const void*
                       const void* shadow, void* workspace, int64_t workspace_bytes, int64_t* counts,
                       void* scores, void* band, void* stream);
 
+/* ---- evaluation batch in one call, filter index resident on the device ---------------------------------
+ * The reference keeps filters[(entity, relation)] -> python list (datasets/process.py:55-77) and walks it per query on the host
+ * (models/base.py:264-268).  Here the whole index lives in HBM as a sorted key table (code = entity * n_rel2 + relation) + CSR
+ * (indptr [n_keys+1], vals: ids sorted and unique inside every list); chk_filter_lookup finds, per query of a batch, its list
+ * (flt_start[i] = start in vals, flt_indptr = prefix sums of the list lengths), subtracts the true tail's own contribution
+ * (counts[i] -= 1 when the tail is NOT in the list and lives in the shard [shard_offset, shard_offset + n_rows); list entries are
+ * the filter pass's job) and sets bit 0 of *flags when a key is missing (the reference raises KeyError, base.py:266). */
+int chk_filter_lookup(const int64_t* queries, int64_t b, int64_t n_rel2, const int64_t* keys, int64_t n_keys,
+                      const int64_t* indptr, const int64_t* vals, int64_t shard_offset, int64_t n_rows,
+                      int64_t* flt_indptr, int64_t* flt_start, int64_t* counts, int32_t* flags, void* stream);
+/* One evaluation batch of KGModel.get_ranking (models/base.py:243-271) enqueued by ONE host call:
+ * ids split -> chk_query_fwd -> chk_row_hnorm -> target scores from the full table -> chk_rank_counts tier `algo` over the shard
+ * -> chk_filter_lookup -> filter pass.  counts [b] (zeroed here) ends as rank-1 of this shard's contribution (sum over shards,
+ * then +1); target [b] holds the true tails' scores (NaN check, base.py:259-260). */
+typedef struct chk_eval_args {
+    int32_t algo, kind, dtype, rank, multi_c, pad_;
+    int64_t b;
+    const int64_t* queries;                               /* [b,3] (head, relation, tail) */
+    const void *entity, *rel, *rel_diag, *ctx, *c_table, *bh, *bt;    /* the model's FULL tables (bh, bt NULL for bias 'none') */
+    const void* hn_full; int64_t n_entities;              /* chk_row_hnorm of the full entity table */
+    const void *shard_entity, *shard_hn, *shard_bt; int64_t shard_rows, shard_offset;   /* this rank's row range */
+    const void* shadow; void* workspace; int64_t workspace_bytes;                       /* CHK_RANK_MMA only */
+    const int64_t *f_keys, *f_indptr, *f_vals; int64_t f_nkeys, n_rel2;                 /* filter index */
+    void* scratch; int64_t scratch_bytes;                 /* chk_eval_scratch_bytes(dtype, rank, b) */
+    int64_t* counts; void* target; int32_t* flags;        /* outputs */
+} chk_eval_args;
+int64_t chk_eval_scratch_bytes(int dtype, int rank, int64_t b);
+int chk_eval_batch(const chk_eval_args* args, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

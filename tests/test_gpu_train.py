@@ -103,7 +103,7 @@ def test_fused_step_matches_contract_path(name, rank, dtype, reg, double_neg, mu
         for pa, pb in zip(a.parameters(), b.parameters()):
             for key in keys:
                 sa, sb = ref.optimizer.state[pa][key], fus.optimizer.state[pb][key]
-                assert (sa - sb).abs().max().item() <= (1e-9 if dbl else 1e-3) * max(sa.abs().max().item(), 1e-30), key
+                assert (sa - sb).abs().max().item() <= (1e-9 if dbl else (1e-3 if rank <= 65 else 5e-3)) * max(sa.abs().max().item(), 1e-30), key
             assert float(fus.optimizer.state[pb]["step"]) == float(ref.optimizer.state[pa]["step"]) == steps
 
 
