@@ -34,7 +34,7 @@ CHK_RED_MAX_COLS, CHK_RED_MAX_GROUPS = 4, 3
 class RedCol(ctypes.Structure):
     """chk_red_col of include/chk_b200.h."""
     _fields_ = [("param", _p), ("state0", _p), ("dense_grad", _p), ("width", _i64), ("src", _p * 2), ("lo", _i64 * 2),
-                ("hi", _i64 * 2), ("rank_stride", _i64 * 2)]
+                ("hi", _i64 * 2), ("rank_stride", _i64 * 2), ("pair_coef", _p), ("pair_nt", _i64), ("coef_rank_stride", _i64)]
 
 
 class RedGroup(ctypes.Structure):
@@ -78,7 +78,7 @@ SIGNATURES = {
     "chk_multi_sparse_adagrad": (_i, [_i, ctypes.POINTER(TableDesc), _i, ctypes.c_double, ctypes.c_double, _p, _p]),
     "chk_scatter_add_rows": (_i, [_i, _p, _p, _p, _i64, _i64, _p]),
     "chk_train_prep": (_i, [_p, _i64, _i64, _i64, _i, _p, _p, ctypes.c_uint64, _p, ctypes.c_uint32, _p, _p, _p, _p]),
-    "chk_score_gather_train": (_i, [_i, _i, _i64, _i64, _p, _i64, _i64, _p, _p, _p, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "chk_score_gather_train": (_i, [_i, _i, _i64, _i64, _p, _i64, _i64, _p, _p, _p, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "chk_group_workspace_bytes": (_i64, [_i64, _i64]),
     "chk_group_build": (_i, [_p, _i64, _i64, _p, _p]),
     "chk_reduce_apply": (_i, [_i, _i, ctypes.POINTER(RedGroup), _i, _p, _i, _p, _i64, _p, _p, _p]),

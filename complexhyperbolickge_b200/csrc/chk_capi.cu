@@ -24,7 +24,7 @@ int chk_rank_counts_mma(int dtype, int rank, int64_t b, const void* q, const voi
                         int64_t n_rows, const void* shadow, void* workspace, int64_t workspace_bytes,
                         int64_t* counts, cudaStream_t st);
 
-extern "C" int chk_abi_version(void) { return 3; }
+extern "C" int chk_abi_version(void) { return 4; }
 extern "C" const char* chk_last_error(void) { return g_err; }
 
 extern "C" int chk_rank_counts(int algo, int dtype, int rank, int64_t b, const void* q, const void* qn,

@@ -29,7 +29,17 @@ template <typename T> struct SArgs {
     T* loss_part;                    // [B] per-row loss partial (already scaled by hyper[2])
     T* gscores;                      // [B, nt] d loss / d score (feeds the bt gradient); g_bh[b] = sum_j of it
     T* g_bh;                         // [B] (one query per row) or NULL (per-pair queries: the bh gradient of a pair is gscores itself)
+    T* pair_coef;                    // MODE 2, optional: [B*nt, 4] = (B1, B2, B3, 0) of every pair INSTEAD of its 2r-wide gradient row
+                                     // (chk_reduce_apply rebuilds grad_w = B1 z + B2 (-i z) - B3 w from the query row and the tail row)
 };
+
+template <typename T> __device__ __forceinline__ void store4(T* p, T a, T b, T c, T d);
+template <> __device__ __forceinline__ void store4<float>(float* p, float a, float b, float c, float d) {
+    *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
+}
+template <> __device__ __forceinline__ void store4<double>(double* p, double a, double b, double c, double d) {
+    reinterpret_cast<double2*>(p)[0] = make_double2(a, b); reinterpret_cast<double2*>(p)[1] = make_double2(c, d);
+}
 
 template <typename T>
 __device__ __forceinline__ T logsigmoid_t(T x) {          // min(x,0) - log1p(exp(-|x|)), as ATen
@@ -148,7 +158,11 @@ __global__ void __launch_bounds__(kWarps * 32, (sizeof(T) == 4 && P <= 5) ? 4 : 
                 // coefficients: 12 flops per complex coefficient instead of 28, and no data-dependent branch inside the loops
                 const T B1 = cw * wn * re1, B2 = cw * wn * im, B3 = cw * mod2;
                 const T A1 = cz * zn * re1, A2 = cz * zn * im, A3 = cz * mod2;
-                if (valid) {
+                if (TRAIN && A.pair_coef) {
+                    if (valid && gl == 0) {
+                        store4<T>(A.pair_coef + pair * 4, B1, B2, B3, T(0));
+                    }
+                } else if (valid) {
                     if (A.grad_dense == nullptr) {
                         T* grow = A.grad_rows + pair * 2 * r;
 #pragma unroll
@@ -367,14 +381,14 @@ template <typename T>
 static int score_gather_train_t(int rank, int64_t B, int64_t nt, const void* q, int64_t q_stride_b, int64_t q_stride_j,
                                 const void* table, const int64_t* tail_idx, const int64_t* head_idx, int64_t head_stride_b,
                                 int64_t head_stride_j, const void* bh, const void* bt, const double* hyper, void* loss_part,
-                                void* grad_scores, void* grad_q, void* grad_rows, void* g_bh, cudaStream_t st) {
+                                void* grad_scores, void* grad_q, void* grad_rows, void* pair_coef, void* g_bh, cudaStream_t st) {
     SArgs<T> A{};
     A.q = (const T*)q; A.q_stride_b = q_stride_b; A.q_stride_j = q_stride_j;
     A.table = (const T*)table; A.tail_idx = tail_idx; A.row_stride_b = 0;
     A.bt = (const T*)bt; A.B = B; A.nt = nt; A.r = rank;
     A.grad_q = (T*)grad_q; A.grad_rows = (T*)grad_rows; A.grad_dense = nullptr;
     A.head_idx = head_idx; A.head_stride_b = head_stride_b; A.head_stride_j = head_stride_j; A.bh_table = (const T*)bh;
-    A.hyper = hyper; A.loss_part = (T*)loss_part; A.gscores = (T*)grad_scores; A.g_bh = (T*)g_bh;
+    A.hyper = hyper; A.loss_part = (T*)loss_part; A.gscores = (T*)grad_scores; A.g_bh = (T*)g_bh; A.pair_coef = (T*)pair_coef;
     return launch_gather<T, 2>(A, st);
 }
 
@@ -383,15 +397,15 @@ extern "C" int chk_score_gather_train(int dtype, int rank, int64_t B, int64_t nt
                                       const void* table, const int64_t* tail_idx,
                                       const int64_t* head_idx, int64_t head_stride_b, int64_t head_stride_j,
                                       const void* bh, const void* bt, const double* hyper,
-                                      void* loss_part, void* grad_scores, void* grad_q, void* grad_rows, void* g_bh,
+                                      void* loss_part, void* grad_scores, void* grad_q, void* grad_rows, void* pair_coef, void* g_bh,
                                       void* stream) {
     if (B == 0 || nt == 0) return CHK_OK;
-    if (B < 0 || nt < 0 || rank < 2 || !q || !table || !tail_idx || !hyper || !loss_part || !grad_scores || !grad_q || !grad_rows ||
+    if (B < 0 || nt < 0 || rank < 2 || !q || !table || !tail_idx || !hyper || !loss_part || !grad_scores || !grad_q || (!grad_rows && !pair_coef) ||
         ((bh == nullptr) != (bt == nullptr)) || (bh && !head_idx)) {
         chk_set_error("chk_score_gather_train: bad argument"); return CHK_EINVAL;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    if (dtype == CHK_F32) return score_gather_train_t<float>(rank, B, nt, q, q_stride_b, q_stride_j, table, tail_idx, head_idx, head_stride_b, head_stride_j, bh, bt, hyper, loss_part, grad_scores, grad_q, grad_rows, g_bh, st);
-    if (dtype == CHK_F64) return score_gather_train_t<double>(rank, B, nt, q, q_stride_b, q_stride_j, table, tail_idx, head_idx, head_stride_b, head_stride_j, bh, bt, hyper, loss_part, grad_scores, grad_q, grad_rows, g_bh, st);
+    if (dtype == CHK_F32) return score_gather_train_t<float>(rank, B, nt, q, q_stride_b, q_stride_j, table, tail_idx, head_idx, head_stride_b, head_stride_j, bh, bt, hyper, loss_part, grad_scores, grad_q, grad_rows, pair_coef, g_bh, st);
+    if (dtype == CHK_F64) return score_gather_train_t<double>(rank, B, nt, q, q_stride_b, q_stride_j, table, tail_idx, head_idx, head_stride_b, head_stride_j, bh, bt, hyper, loss_part, grad_scores, grad_q, grad_rows, pair_coef, g_bh, st);
     chk_set_error("unknown dtype %d", dtype); return CHK_EINVAL;
 }

@@ -139,6 +139,7 @@ constexpr int SORT_CAP = 4096;            // slots of a long segment the CTA sor
 template <typename T> struct RCol {
     T* param; T* s0; T* dense; int width;
     const T* src[2]; int lo[2], hi[2]; int64_t rstride[2];
+    const T* coef; int pair_nt; int64_t cstride;      // computed source (see chk_red_col): src[1] = query rows, coef = (c1, c2, c3, pad) per pair
 };
 template <typename T> struct RGroup {
     GroupView v; const int64_t* ids; int slots_per_rank; int total; int n_cols; int single;   // single: every slot names row 0 (no grouping)
@@ -507,7 +508,238 @@ __device__ __forceinline__ void fast_entity_phase1(const RGroup<T>& G, T lr, T e
     }
 }
 
-template <typename T, int W2>
+
+// ---- computed-source path of the entity-keyed group ----------------------------------------------------------------
+// The tail-row gradient of a (query, tail) pair is rebuilt from the pair's three scalars, the query row z and the tail row w
+// the warp is about to update, with the operations K3 would have used to store it (bit-identical to the stored-row path):
+//     g_re[k] = fma(c1, z_re[k], fma(c2, z_im[k], -c3 * w_re[k])),   g_im[k] = fma(c1, z_im[k], fma(-c2, z_re[k], -c3 * w_im[k]))
+// so a pair costs 16 bytes (+ an L2-resident query row) instead of a 2R-wide row written by K3, read here and — data parallel —
+// all_gathered.  Lane l owns the complex coefficients k = 32 c + l of chunk c: elements k and R + k of the row.
+template <typename T> struct CoefSrc {
+    const T* src0; const T* qsrc; const T* coef; int64_t rs0, rsq, cs; int hi0, lo1, nt, spr;
+};
+template <typename T> struct V4;
+template <> struct V4<float> { using type = float4; };
+template <> struct V4<double> { using type = double4; };
+
+// descriptor of slot s: stored row (head-entity gradient of the K1 adjoint) or pair (query row + coefficients)
+template <typename T, int R>
+__device__ __forceinline__ void coef_desc(const CoefSrc<T>& C, int s, bool live, const T*& dp, T& d1, T& d2, T& d3, bool& pair) {
+    dp = nullptr; d1 = T(0); d2 = T(0); d3 = T(0); pair = false;
+    if (!live) return;
+    int rk = 0, ls = s;
+    if (s >= C.spr) { rk = s / C.spr; ls = s - rk * C.spr; }
+    if (ls < C.hi0) { dp = C.src0 + rk * C.rs0 + (int64_t)ls * (2 * R); return; }
+    const int pi = ls - C.lo1;
+    const int qi = C.nt ? pi / C.nt : pi;
+    dp = C.qsrc + rk * C.rsq + (int64_t)qi * (2 * R);
+    const T* cf = C.coef + rk * C.cs + (int64_t)pi * 4;
+    if constexpr (sizeof(T) == 4) { const float4 v = *reinterpret_cast<const float4*>(cf); d1 = v.x; d2 = v.y; d3 = v.z; }
+    else { const double2 a = reinterpret_cast<const double2*>(cf)[0]; d1 = a.x; d2 = a.y; d3 = cf[2]; }
+    pair = true;
+}
+template <typename T>
+__device__ __forceinline__ T shfl_val(T v, int k) {
+    if constexpr (sizeof(T) == 4) return __shfl_sync(CHK_FULL, v, k);
+    else {
+        const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+        const unsigned lo = __shfl_sync(CHK_FULL, (unsigned)b, k), hi = __shfl_sync(CHK_FULL, (unsigned)(b >> 32), k);
+        return __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
+    }
+}
+template <int R, int C0, int H>
+__device__ __forceinline__ bool coef_on(int lane) { return (C0 + H) * 32 + 32 <= R || lane < R - (C0 + H) * 32; }
+
+// adds the contributions of the (<= 32) slots described lane-wise by (dp, d1, d2, d3, pairmask) to (ar, ai), in lane order,
+// for complex chunks C0 .. C0+CNT-1; (wr, wi) = the row's current values of those coefficients
+template <typename T, int R, int C0, int CNT>
+__device__ __forceinline__ void coef_accumulate(T (&ar)[CNT], T (&ai)[CNT], const T (&wr)[CNT], const T (&wi)[CNT], int len, int lane,
+                                                const T* dp, T d1, T d2, T d3, unsigned pairmask) {
+    constexpr int U = CNT <= 2 ? 4 : (CNT <= 3 ? 2 : 1);                 // slots in flight
+    for (int k = 0; k < len; k += U) {
+        T zr[U][CNT], zi[U][CNT], c1[U], c2[U], c3[U];
+        bool pr[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int kk = (k + u) & 31;
+            const T* p = shfl_ptr<T>(dp, kk);
+            c1[u] = shfl_val<T>(d1, kk); c2[u] = shfl_val<T>(d2, kk); c3[u] = shfl_val<T>(d3, kk);
+            pr[u] = (pairmask >> kk) & 1u;
+            const bool live = k + u < len;
+#pragma unroll
+            for (int h = 0; h < CNT; ++h) {
+                const bool on = live && ((C0 + h) * 32 + 32 <= R || lane < R - (C0 + h) * 32);
+                zr[u][h] = T(0); zi[u][h] = T(0);
+                if (on) { zr[u][h] = p[(C0 + h) * 32 + lane]; zi[u][h] = p[R + (C0 + h) * 32 + lane]; }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int h = 0; h < CNT; ++h) {
+                const T gr = Sc<T>::fma_(c1[u], zr[u][h], Sc<T>::fma_(c2[u], zi[u][h], -c3[u] * wr[h]));
+                const T gi = Sc<T>::fma_(c1[u], zi[u][h], Sc<T>::fma_(-c2[u], zr[u][h], -c3[u] * wi[h]));
+                ar[h] += pr[u] ? gr : zr[u][h];
+                ai[h] += pr[u] ? gi : zi[u][h];
+            }
+    }
+}
+template <typename T, int R, int C0, int CNT>
+__device__ __forceinline__ void coef_load_row(const T* __restrict__ base, int64_t rowoff, int lane, T (&xr)[CNT], T (&xi)[CNT]) {
+#pragma unroll
+    for (int h = 0; h < CNT; ++h) {
+        const bool on = (C0 + h) * 32 + 32 <= R || lane < R - (C0 + h) * 32;
+        xr[h] = T(0); xi[h] = T(0);
+        if (on) { xr[h] = base[rowoff + (C0 + h) * 32 + lane]; xi[h] = base[rowoff + R + (C0 + h) * 32 + lane]; }
+    }
+}
+template <typename T, int R, int C0, int CNT>
+__device__ __forceinline__ void coef_finish(T* __restrict__ param, T* __restrict__ st, T* __restrict__ dense, int64_t rowoff, int lane,
+                                            T (&ar)[CNT], T (&ai)[CNT], T (&wr)[CNT], T (&wi)[CNT], T (&sr)[CNT], T (&si)[CNT], T lr, T eps) {
+#pragma unroll
+    for (int h = 0; h < CNT; ++h) {
+        const bool on = (C0 + h) * 32 + 32 <= R || lane < R - (C0 + h) * 32;
+        if (!on) continue;
+        const int64_t e = rowoff + (C0 + h) * 32 + lane;
+        if (dense) { dense[e] = ar[h]; dense[e + R] = ai[h]; }
+        else {
+            adagrad_apply<T>(wr[h], ar[h], sr[h], lr, eps); adagrad_apply<T>(wi[h], ai[h], si[h], lr, eps);
+            param[e] = wr[h]; param[e + R] = wi[h]; st[e] = sr[h]; st[e + R] = si[h];
+        }
+    }
+}
+// one warp, one short segment, chunks C0 .. C0+CNT-1
+template <typename T, int R, int C0, int CNT>
+__device__ __forceinline__ void coef_pass(T* __restrict__ param, T* __restrict__ st, T* __restrict__ dense, int64_t rowoff, int len, int lane,
+                                          const T* dp, T d1, T d2, T d3, unsigned pairmask, T lr, T eps) {
+    T ar[CNT], ai[CNT], wr[CNT], wi[CNT], sr[CNT], si[CNT];
+    coef_load_row<T, R, C0, CNT>(param, rowoff, lane, wr, wi);
+    if (!dense) coef_load_row<T, R, C0, CNT>(st, rowoff, lane, sr, si);
+#pragma unroll
+    for (int h = 0; h < CNT; ++h) { ar[h] = T(0); ai[h] = T(0); }
+    coef_accumulate<T, R, C0, CNT>(ar, ai, wr, wi, len, lane, dp, d1, d2, d3, pairmask);
+    coef_finish<T, R, C0, CNT>(param, st, dense, rowoff, lane, ar, ai, wr, wi, sr, si, lr, eps);
+}
+
+template <typename T, int R>
+__device__ __forceinline__ CoefSrc<T> coef_src_of(const RGroup<T>& G) {
+    const RCol<T>& c0 = G.col[0];
+    CoefSrc<T> C;
+    C.src0 = c0.src[0]; C.qsrc = c0.src[1]; C.coef = c0.coef; C.rs0 = c0.rstride[0]; C.rsq = c0.rstride[1]; C.cs = c0.cstride;
+    C.hi0 = c0.hi[0]; C.lo1 = c0.lo[1]; C.nt = c0.pair_nt; C.spr = G.slots_per_rank;
+    return C;
+}
+
+// short segments (<= 32 slots) of the entity group, one warp per segment (same walk as fast_entity_phase1)
+template <typename T, int R>
+__device__ __forceinline__ void coef_entity_phase1(const RGroup<T>& G, T lr, T eps, int lane, int gwarp, int nwarps) {
+    constexpr int NCH = (R + 31) / 32;
+    const RCol<T>& c0 = G.col[0];
+    const CoefSrc<T> C = coef_src_of<T, R>(G);
+    T* const param = c0.param; T* const st = c0.s0; T* const dense = c0.dense;
+    const int spr = G.slots_per_rank, nsc = G.n_cols - 1;
+    const int nshort = G.v.hdr[0];
+    auto meta = [&](int sg, int& id, int& len, int& base) {
+        id = 0; len = 0; base = 0;
+        if (sg < nshort) { id = G.v.seg[sg]; len = G.v.slen[sg]; base = G.v.sbase[sg]; }
+    };
+    int id0, len0, base0, id1, len1, base1, mine0 = 0x7fffffff, mine1;
+    meta(gwarp, id0, len0, base0);
+    meta(gwarp + nwarps, id1, len1, base1);
+    if (lane < len0) mine0 = G.v.order[base0 + lane];
+    for (int sg = gwarp; sg < nshort; sg += nwarps) {
+        int id2, len2, base2;
+        meta(sg + 2 * nwarps, id2, len2, base2);
+        mine1 = 0x7fffffff;
+        if (lane < len1) mine1 = G.v.order[base1 + lane];
+        const int id = id0, len = len0;
+        const int mine = warp_sort_len(mine0, lane, len);
+        const T* dp; T d1, d2, d3; bool pair;
+        coef_desc<T, R>(C, mine, lane < len, dp, d1, d2, d3, pair);
+        const unsigned pairmask = __ballot_sync(CHK_FULL, pair);
+        int rk = 0, ls = mine;
+        if (lane < len && mine >= spr) { rk = mine / spr; ls = mine - rk * spr; }
+        T sp[2], sa[2], sv[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            sp[j] = T(0); sa[j] = T(0); sv[j] = T(0);
+            if (j < nsc) {
+                const RCol<T>& c = G.col[1 + j];
+                if (lane == 0 && !c.dense) { sp[j] = c.param[id]; sa[j] = c.s0[id]; }
+                if (lane < len && ls >= c.lo[0] && ls < c.hi[0]) sv[j] = c.src[0][rk * c.rstride[0] + (ls - c.lo[0])];
+            }
+        }
+        const int64_t rowoff = (int64_t)id * (2 * R);
+        if constexpr (NCH <= 5) coef_pass<T, R, 0, (NCH <= 5 ? NCH : 1)>(param, st, dense, rowoff, len, lane, dp, d1, d2, d3, pairmask, lr, eps);
+        else {
+            coef_pass<T, R, 0, 5>(param, st, dense, rowoff, len, lane, dp, d1, d2, d3, pairmask, lr, eps);
+            coef_pass<T, R, 5, (NCH > 5 ? NCH - 5 : 1)>(param, st, dense, rowoff, len, lane, dp, d1, d2, d3, pairmask, lr, eps);
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            if (j < nsc) {
+                const RCol<T>& c = G.col[1 + j];
+                const T g = warp_sum<T>(sv[j]);
+                if (lane == 0) {
+                    if (c.dense) c.dense[id] = g;
+                    else { T pp = sp[j], aa = sa[j]; adagrad_apply<T>(pp, g, aa, lr, eps); c.param[id] = pp; c.s0[id] = aa; }
+                }
+            }
+        }
+        id0 = id1; len0 = len1; base0 = base1; mine0 = mine1;
+        id1 = id2; len1 = len2; base1 = base2;
+    }
+}
+
+// long segment (> 32 slots) of the entity group, one CTA: every warp sums a contiguous eighth of the sorted slots (32 at a
+// time through the lane-wise descriptors), warp 0 adds the eight partials in warp order and applies the update — the same
+// order of additions as the stored-row path.  `cpart` = [RWARPS][2 * CMAX][32] partials.
+template <typename T, int R, int C0, int CNT>
+__device__ __forceinline__ void coef_long_pass(const CoefSrc<T>& C, T* __restrict__ param, T* __restrict__ st, T* __restrict__ dense, int64_t rowoff,
+                                               const int* sorted, int k_lo, int k_hi, int lane, int warp, T* cpart, T lr, T eps) {
+    T ar[CNT], ai[CNT], wr[CNT], wi[CNT], sr[CNT], si[CNT];
+    coef_load_row<T, R, C0, CNT>(param, rowoff, lane, wr, wi);
+#pragma unroll
+    for (int h = 0; h < CNT; ++h) { ar[h] = T(0); ai[h] = T(0); }
+    for (int k0 = k_lo; k0 < k_hi; k0 += 32) {
+        const int n = min(32, k_hi - k0);
+        const T* dp; T d1, d2, d3; bool pair;
+        coef_desc<T, R>(C, lane < n ? sorted[k0 + lane] : 0, lane < n, dp, d1, d2, d3, pair);
+        const unsigned pairmask = __ballot_sync(CHK_FULL, pair);
+        coef_accumulate<T, R, C0, CNT>(ar, ai, wr, wi, n, lane, dp, d1, d2, d3, pairmask);
+    }
+    __syncthreads();                                                       // cpart of the previous pass / segment is free
+#pragma unroll
+    for (int h = 0; h < CNT; ++h) { cpart[(warp * 2 * CNT + 2 * h) * 32 + lane] = ar[h]; cpart[(warp * 2 * CNT + 2 * h + 1) * 32 + lane] = ai[h]; }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int h = 0; h < CNT; ++h) {
+            T a = cpart[(2 * h) * 32 + lane], b = cpart[(2 * h + 1) * 32 + lane];
+#pragma unroll
+            for (int w = 1; w < RWARPS; ++w) { a += cpart[(w * 2 * CNT + 2 * h) * 32 + lane]; b += cpart[(w * 2 * CNT + 2 * h + 1) * 32 + lane]; }
+            ar[h] = a; ai[h] = b;
+        }
+        if (!dense) coef_load_row<T, R, C0, CNT>(st, rowoff, lane, sr, si);
+        coef_finish<T, R, C0, CNT>(param, st, dense, rowoff, lane, ar, ai, wr, wi, sr, si, lr, eps);
+    }
+}
+template <typename T, int R>
+__device__ __forceinline__ void coef_long_segment(const RGroup<T>& G, int id, int len, const int* sorted, int lane, int warp, T* cpart, T lr, T eps) {
+    constexpr int NCH = (R + 31) / 32;
+    const RCol<T>& c0 = G.col[0];
+    const CoefSrc<T> C = coef_src_of<T, R>(G);
+    const int per = (len + RWARPS - 1) / RWARPS;
+    const int k_lo = min(warp * per, len), k_hi = min(k_lo + per, len);
+    const int64_t rowoff = (int64_t)id * (2 * R);
+    if constexpr (NCH <= 5) coef_long_pass<T, R, 0, (NCH <= 5 ? NCH : 1)>(C, c0.param, c0.s0, c0.dense, rowoff, sorted, k_lo, k_hi, lane, warp, cpart, lr, eps);
+    else {
+        coef_long_pass<T, R, 0, 5>(C, c0.param, c0.s0, c0.dense, rowoff, sorted, k_lo, k_hi, lane, warp, cpart, lr, eps);
+        coef_long_pass<T, R, 5, (NCH > 5 ? NCH - 5 : 1)>(C, c0.param, c0.s0, c0.dense, rowoff, sorted, k_lo, k_hi, lane, warp, cpart, lr, eps);
+    }
+}
+
+template <typename T, int W2, bool COEF>
 __global__ void __launch_bounds__(RWARPS * 32, (W2 > 0 && W2 <= 65) || W2 == 0 ? 4 : 3) reduce_apply_kernel(const RArgsStep<T> A) {
     using V = typename V2<T>::type;
     constexpr int MAXCH = 2;
@@ -537,7 +769,8 @@ __global__ void __launch_bounds__(RWARPS * 32, (W2 > 0 && W2 <= 65) || W2 == 0 ?
         int nshort = G.single ? 0 : G.v.hdr[0];
         if constexpr (W2 > 0) {                                        // compile-time-width fast path for the entity-keyed group
             if (gi == 0) {
-                fast_entity_phase1<T, W2>(G, lr, eps, lane, gwarp, nwarps);
+                if constexpr (COEF) coef_entity_phase1<T, W2>(G, lr, eps, lane, gwarp, nwarps);
+                else fast_entity_phase1<T, W2>(G, lr, eps, lane, gwarp, nwarps);
                 nshort = 0;
             }
         }
@@ -635,6 +868,13 @@ __global__ void __launch_bounds__(RWARPS * 32, (W2 > 0 && W2 <= 65) || W2 == 0 ?
             for (int ci = 0; ci < G.n_cols; ++ci) {
                 const RCol<T>& c = G.col[ci];
                 if (c.width == 1) { if (warp == 0) col_scalar<T>(c, id, len, spr, lr, eps, lane, slot_at); continue; }
+                if constexpr (COEF && W2 > 0) {
+                    if (gi == 0 && ci == 0) {                              // pairs are rebuilt from their coefficients
+                        __shared__ T cpart[RWARPS * 2 * 5 * 32];
+                        coef_long_segment<T, W2>(G, id, len, sorted, lane, warp, cpart, lr, eps);
+                        continue;
+                    }
+                }
                 const int w2 = c.width >> 1, nch = (w2 + 31) >> 5;
                 const int64_t rowoff = (int64_t)id * c.width;
                 for (int ch = 0; ch < nch; ++ch) {
@@ -856,6 +1096,8 @@ static int reduce_apply_t(int opt, const chk_red_group* groups, int n_groups, co
             RCol<T>& C = R.col[ci];
             C.param = (T*)c.param; C.s0 = (T*)c.state0; C.dense = (T*)c.dense_grad; C.width = (int)c.width;
             for (int i = 0; i < 2; ++i) { C.src[i] = (const T*)c.src[i]; C.lo[i] = (int)c.lo[i]; C.hi[i] = (int)c.hi[i]; C.rstride[i] = c.rank_stride[i]; }
+            C.coef = (const T*)c.pair_coef; C.pair_nt = (int)c.pair_nt; C.cstride = c.coef_rank_stride;
+            if (c.pair_coef && (gi != 0 || ci != 0 || c.pair_nt < 0)) { chk_set_error("chk_reduce_apply: pair_coef is for the first column of group 0"); return CHK_EINVAL; }
         }
         if (!g.single_row && g.n_keys * 0 + total > max_seg) max_seg = total;
     }
@@ -872,16 +1114,21 @@ static int reduce_apply_t(int opt, const chk_red_group* groups, int n_groups, co
         for (int ci = 1; ci < g0.n_cols && ok; ++ci) ok = g0.cols[ci].width == 1 && g0.cols[ci].src[0] && !g0.cols[ci].src[1];
         if (ok) w2 = (int)(c0.width >> 1);
     }
-    const int grid4 = grid_for(max_seg, RWARPS, 148 * 4), grid3 = grid_for(max_seg, RWARPS, 148 * 3);
-    switch (w2) {
-        case 9: reduce_apply_kernel<T, 9><<<grid4, RWARPS * 32, 0, st>>>(A); break;
-        case 17: reduce_apply_kernel<T, 17><<<grid4, RWARPS * 32, 0, st>>>(A); break;
-        case 33: reduce_apply_kernel<T, 33><<<grid4, RWARPS * 32, 0, st>>>(A); break;
-        case 65: reduce_apply_kernel<T, 65><<<grid4, RWARPS * 32, 0, st>>>(A); break;
-        case 129: reduce_apply_kernel<T, 129><<<grid3, RWARPS * 32, 0, st>>>(A); break;
-        case 257: reduce_apply_kernel<T, 257><<<grid3, RWARPS * 32, 0, st>>>(A); break;
-        default: reduce_apply_kernel<T, 0><<<grid4, RWARPS * 32, 0, st>>>(A); break;
+    const bool coef = groups[0].cols[0].pair_coef != nullptr;
+    if (coef && !(w2 == 9 || w2 == 17 || w2 == 33 || w2 == 65 || w2 == 129 || w2 == 257)) {
+        chk_set_error("chk_reduce_apply: pair_coef needs the entity-group shape and a rank in {9,17,33,65,129,257}"); return CHK_EINVAL;
     }
+    const int grid4 = grid_for(max_seg, RWARPS, 148 * 4), grid3 = grid_for(max_seg, RWARPS, 148 * 3);
+#define CHK_RED_LAUNCH(W, G)                                                                                   \
+    case W: if (coef) reduce_apply_kernel<T, W, true><<<G, RWARPS * 32, 0, st>>>(A);                          \
+            else reduce_apply_kernel<T, W, false><<<G, RWARPS * 32, 0, st>>>(A);                              \
+            break;
+    switch (w2) {
+        CHK_RED_LAUNCH(9, grid4) CHK_RED_LAUNCH(17, grid4) CHK_RED_LAUNCH(33, grid4) CHK_RED_LAUNCH(65, grid4)
+        CHK_RED_LAUNCH(129, grid3) CHK_RED_LAUNCH(257, grid3)
+        default: reduce_apply_kernel<T, 0, false><<<grid4, RWARPS * 32, 0, st>>>(A); break;
+    }
+#undef CHK_RED_LAUNCH
     CHK_CUDA_LAUNCH_CHECK("reduce_apply_kernel");
     return CHK_OK;
 }

@@ -473,12 +473,14 @@ def train_prep(batch, neg, n_entities, double_neg, seed, step_id, stream_id, hea
 
 
 def score_gather_train(rank, B, nt, q, q_stride_b, q_stride_j, table, tail_idx, head_idx, head_stride_b, head_stride_j, bh, bt,
-                       hyper, loss_part, grad_scores, grad_q, grad_rows, g_bh):
-    """K3 training pass: scores + negative-sampling loss terms + adjoint (all outputs preallocated)."""
-    _chk(q, table, tail_idx, head_idx, bh, bt, hyper, loss_part, grad_scores, grad_q, grad_rows, g_bh)
+                       hyper, loss_part, grad_scores, grad_q, grad_rows, g_bh, pair_coef=None):
+    """K3 training pass: scores + negative-sampling loss terms + adjoint (all outputs preallocated).  pair_coef [B*nt, 4]:
+    the tail-row gradients are left as three scalars per pair for chk_reduce_apply to rebuild (grad_rows may be None)."""
+    _chk(q, table, tail_idx, head_idx, bh, bt, hyper, loss_part, grad_scores, grad_q, grad_rows, g_bh, pair_coef)
     _lib.check(_lib.lib().chk_score_gather_train(_dt(q), rank, B, nt, _p(q), q_stride_b, q_stride_j, _p(table), _p(tail_idx),
                                                  _p(head_idx), head_stride_b, head_stride_j, _p(bh), _p(bt), _p(hyper),
-                                                 _p(loss_part), _p(grad_scores), _p(grad_q), _p(grad_rows), _p(g_bh), _stream()),
+                                                 _p(loss_part), _p(grad_scores), _p(grad_q), _p(grad_rows), _p(pair_coef), _p(g_bh),
+                                                 _stream()),
                "chk_score_gather_train")
     _launched(1)
 
@@ -523,6 +525,10 @@ def _red_groups(groups):
             for i, (t, lo, hi, rs) in enumerate(c["src"]):
                 _chk(t)
                 C.src[i], C.lo[i], C.hi[i], C.rank_stride[i] = _p(t), lo, hi, rs
+            pc = c.get("pair")                                   # (coef tensor, pair_nt, coef_rank_stride): src[1] holds query rows
+            if pc is not None:
+                _chk(pc[0])
+                C.pair_coef, C.pair_nt, C.coef_rank_stride = _p(pc[0]), pc[1], pc[2]
     return arr
 
 

@@ -195,7 +195,8 @@ class FusedDataParallelKGOptimizer(FusedKGOptimizer):
             pl.ent_group_ids, pl.ent_group_slots = pl.all_ids.view(-1), W * S_e
             f0, off = pl.all_flat[0], pl.offsets
             sp_col = lambda p, *src: dict(param=p.data, state0=self._state_of(p), dense=None, src=list(src))
-            ecols = [sp_col(m.entity.weight, (f0[off["g_ent"]:], 0, Bq, L), (f0[off["grow"]:], Bq, S_e, L))]
+            esrc, epair = self._entity_sources(pl, (f0[off["g_ent"]:], 0, Bq, L), rank_stride=L, base=f0)
+            ecols = [dict(sp_col(m.entity.weight, *esrc), pair=epair)]
             if m.bias == "learn":
                 ecols.append(sp_col(m.bh.weight, (f0[off["gs" if pl.dn else "g_bh"]:], 0, Bq, L)))
                 ecols.append(sp_col(m.bt.weight, (f0[off["gs"]:], Bq, S_e, L)))
@@ -203,7 +204,8 @@ class FusedDataParallelKGOptimizer(FusedKGOptimizer):
         else:
             pl.w_ent = ops.group_workspace(N, S_e, dev)
             pl.ent_group_ids, pl.ent_group_slots = pl.ent_ids, S_e
-            ecols = [dense_col(m.entity.weight, (pl.g_ent, 0, Bq, 0), (pl.grow, Bq, S_e, 0))]
+            esrc, epair = self._entity_sources(pl, (pl.g_ent, 0, Bq, 0))
+            ecols = [dict(dense_col(m.entity.weight, *esrc), pair=epair)]
             if m.bias == "learn":
                 ecols.append(dense_col(m.bh.weight, (pl.gs if pl.dn else pl.g_bh, 0, Bq, 0)))
                 ecols.append(dense_col(m.bt.weight, (pl.gs, Bq, S_e, 0)))

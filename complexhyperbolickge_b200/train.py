@@ -57,18 +57,32 @@ class _Plan:
         self.rels_b = self.rels if not self.dn else torch.zeros((B,), **i64)
         att = m._ctx_weight() is not None
         wrd = m.rel_diag.weight.shape[1]
-        # contributions of the entity group live in ONE flat buffer (it is what travels in the data-parallel exchange)
-        o_ent, o_row, o_gs = 0, _round4(Bq * 2 * r), 0
-        o_gs = o_row + _round4(P * 2 * r)
+        # contributions of the entity group live in ONE flat buffer (it is what travels in the data-parallel exchange):
+        #   stored rows:        [ g_ent Bq x 2r | grow P x 2r          | gs P | g_bh B ]
+        #   pair coefficients:  [ g_ent Bq x 2r | q Bq x 2r | coef P x 4 | gs P | g_bh B ]   (tail-row gradients rebuilt by the reduce)
+        self.coef_mode = o._pair_coef_mode()
+        mk = lambda *s: torch.zeros(s, dtype=dt, device=dev)
+        o_ent, o_row = 0, _round4(Bq * 2 * r)
+        if self.coef_mode:
+            o_coef = o_row + _round4(Bq * 2 * r)
+            o_gs = o_coef + P * 4
+        else:
+            o_coef = None
+            o_gs = o_row + _round4(P * 2 * r)
         o_bh = o_gs + _round4(P)
         flat_len = o_bh + (0 if self.dn else _round4(B))
         self.flat = torch.zeros((flat_len,), dtype=dt, device=dev)
         self.g_ent = self.flat[o_ent:o_ent + Bq * 2 * r].view(Bq, 2 * r)
-        self.grow = self.flat[o_row:o_row + P * 2 * r].view(P, 2 * r)
+        if self.coef_mode:
+            self.q = self.flat[o_row:o_row + Bq * 2 * r].view(Bq, 2 * r)
+            self.coef = self.flat[o_coef:o_coef + P * 4].view(P, 4)
+            self.grow = None
+        else:
+            self.q, self.coef = mk(Bq, 2 * r), None
+            self.grow = self.flat[o_row:o_row + P * 2 * r].view(P, 2 * r)
         self.gs = self.flat[o_gs:o_gs + P].view(B, nt)
         self.g_bh = None if self.dn else self.flat[o_bh:o_bh + B]
-        mk = lambda *s: torch.zeros(s, dtype=dt, device=dev)
-        self.q, self.c_out, self.grad_q = mk(Bq, 2 * r), mk(Bq), mk(Bq, 2 * r)
+        self.c_out, self.grad_q = mk(Bq), mk(Bq, 2 * r)
         self.g_rel, self.g_rd, self.g_c = mk(Bq, 2 * n), mk(Bq, wrd), mk(Bq)
         self.g_ctx = mk(Bq, n) if att else None
         if self.dn:                                       # per-pair relation-row gradients are summed over j first
@@ -80,13 +94,19 @@ class _Plan:
         self.inj_t = self.inj_h = None
         self.S_e = Bq + P                                 # entity-group slots per rank
         self.graph = None
-        self.offsets = dict(g_ent=o_ent, grow=o_row, gs=o_gs, g_bh=o_bh)      # element offsets inside ``flat``
+        self.offsets = dict(g_ent=o_ent, grow=o_row, q=o_row, coef=o_coef, gs=o_gs, g_bh=o_bh)      # element offsets inside ``flat``
         o._build_groups(self)
 
 
 class FusedKGOptimizer(KGOptimizer):
-    def __init__(self, *args, use_cuda_graph: bool = True, seed=None, **kw):
+    PAIR_COEF_RANKS = (9, 17, 33, 65, 129, 257)      # ranks chk_reduce_apply has a computed-source instantiation for
+
+    def __init__(self, *args, use_cuda_graph: bool = True, seed=None, pair_coef=None, **kw):
+        """pair_coef: None = rebuild the tail-row gradients in the reduce from three scalars per pair whenever that path
+        exists (rank in PAIR_COEF_RANKS, no N3 / F2 term on the tail rows); False = always store the rows (the two are
+        bit-identical; tests compare them)."""
         super().__init__(*args, **kw)
+        self._pair_coef = pair_coef
         m = self.model
         w = getattr(self.regularizer, "weight", None)
         kind = type(self.regularizer).__name__
@@ -142,6 +162,21 @@ class FusedKGOptimizer(KGOptimizer):
     def _state_of(self, p):
         return self.optimizer.state[p]["sum"]
 
+    def _pair_coef_mode(self) -> bool:
+        ok = self.model.rank in self.PAIR_COEF_RANKS and self._reg is None
+        if self._pair_coef and not ok:
+            raise ValueError("pair_coef=True needs a rank in %s and no N3 / F2 regulariser" % (self.PAIR_COEF_RANKS,))
+        return ok if self._pair_coef is None else bool(self._pair_coef)
+
+    def _entity_sources(self, pl, head_src, rank_stride=0, base=None):
+        """(src list, pair descriptor) of the entity column: head-entity gradient rows + tail contributions (stored rows or
+        query rows + pair coefficients).  base: a flat tensor holding rank 0's buffer (data parallel) or None (plan views)."""
+        Bq, S_e, off = pl.Bq, pl.S_e, pl.offsets
+        view = (lambda name, t: t) if base is None else (lambda name, t: base[off[name]:])
+        if pl.coef_mode:
+            return ([head_src, (view("q", pl.q), Bq, S_e, rank_stride)], (view("coef", pl.coef), 0 if pl.dn else pl.nt, rank_stride))
+        return [head_src, (view("grow", pl.grow), Bq, S_e, rank_stride)], None
+
     def _injected_sampler(self):
         return type(self).get_neg_samples is not KGOptimizer.get_neg_samples
 
@@ -173,7 +208,8 @@ class FusedKGOptimizer(KGOptimizer):
 
         def col(p, *src):
             return dict(param=p.data, state0=self._state_of(p) if inplace else None, dense=None if inplace else p.grad, src=list(src))
-        ecols = [col(m.entity.weight, (pl.g_ent, 0, Bq, 0), (pl.grow, Bq, S_e, 0))]
+        esrc, epair = self._entity_sources(pl, (pl.g_ent, 0, Bq, 0))
+        ecols = [dict(col(m.entity.weight, *esrc), pair=epair)]
         if m.bias == "learn":
             ecols.append(col(m.bh.weight, (pl.gs if pl.dn else pl.g_bh, 0, Bq, 0)))
             ecols.append(col(m.bt.weight, (pl.gs, Bq, S_e, 0)))
@@ -226,7 +262,7 @@ class FusedKGOptimizer(KGOptimizer):
         qsb, qsj = (nt, 1) if pl.dn else (1, 0)
         ops.score_gather_train(r, B, nt, pl.q, qsb, qsj, ent, pl.tails, pl.heads if learn else None, qsb, qsj,
                                m.bh.weight.data.view(-1) if learn else None, m.bt.weight.data.view(-1) if learn else None,
-                               self._hyper, pl.loss_part, pl.gs, pl.grad_q, pl.grow, pl.g_bh if learn else None)
+                               self._hyper, pl.loss_part, pl.gs, pl.grad_q, pl.grow, pl.g_bh if learn else None, pair_coef=pl.coef)
         ops.query_bwd_into(m.KIND, r, bool(m.multi_c), ent, rel, rd, ctx, cw, pl.heads, pl.rels, pl.grad_q, pl.g_ent, pl.g_rel,
                            pl.g_rd, pl.g_ctx, pl.g_c)
         if pl.dn:

@@ -161,13 +161,18 @@ int chk_train_prep(const int64_t* batch, int64_t B, int64_t neg, int64_t n_entit
  * positive: -logsigmoid(s), others -logsigmoid(-s), scaled by hyper[2]) and the adjoint, tail rows gathered once.
  * Out: loss_part [B] (row sums of the scaled terms), grad_scores [B,nt] (= the bt gradient of every pair), grad_q (strides of q;
  * reduced over j when q_stride_j == 0), grad_rows [B*nt,2r], g_bh [B] (sum_j grad_scores; NULL with per-pair queries).
+ * pair_coef (optional, [B*nt,4]): when given, the tail-row gradient of a pair is NOT stored (grad_rows may be NULL); the kernel
+ * writes its three pair scalars (c1, c2, c3, 0) and chk_reduce_apply rebuilds the row from them, the query row z and the tail
+ * row w it updates:  g_re[k] = c1 z_re[k] + c2 z_im[k] - c3 w_re[k],  g_im[k] = c1 z_im[k] - c2 z_re[k] - c3 w_im[k]
+ * (same operations, same order as the stored row: bit-identical).  16 bytes per pair instead of 8r (4r in fp32).
  * bias: bh value of pair (b,j) = bh[head_idx[b*head_stride_b + j*head_stride_j]]; bh/bt both NULL for bias 'none'. */
 int chk_score_gather_train(int dtype, int rank, int64_t B, int64_t nt,
                            const void* q, int64_t q_stride_b, int64_t q_stride_j,
                            const void* table, const int64_t* tail_idx,
                            const int64_t* head_idx, int64_t head_stride_b, int64_t head_stride_j,
                            const void* bh, const void* bt, const double* hyper,
-                           void* loss_part, void* grad_scores, void* grad_q, void* grad_rows, void* g_bh, void* stream);
+                           void* loss_part, void* grad_scores, void* grad_q, void* grad_rows, void* pair_coef, void* g_bh,
+                           void* stream);
 
 /* Grouping of `total_slots` slots by the table row they name (ids[s] in [0, n_keys)): fills the workspace (int32, size
  * chk_group_workspace_bytes, zero-initialised once by the caller; chk_reduce_apply / chk_step_finish leave it ready for
@@ -187,6 +192,12 @@ int chk_group_build(const int64_t* ids, int64_t total_slots, int64_t n_keys, voi
 typedef struct chk_red_col {
     void* param; void* state0; void* dense_grad; int64_t width;
     const void* src[2]; int64_t lo[2], hi[2], rank_stride[2];
+    /* Computed source (pair_coef NULL = off; first column of group 0 only, rank in {9,17,33,65,129,257}): the slots
+     * [lo[1], hi[1]) are (query, tail) pairs whose contribution row is rebuilt, not read: src[1] holds the QUERY rows
+     * ([re | im], `width` elements, rank_stride[1] between ranks) and pair_coef the (c1, c2, c3, pad) chk_score_gather_train
+     * wrote per pair (coef_rank_stride elements between ranks).  Pair p = slot - lo[1] uses query row p / pair_nt
+     * (pair_nt >= 1: one query per pair_nt pairs) or p (pair_nt == 0: per-pair queries, double_neg). */
+    const void* pair_coef; int64_t pair_nt; int64_t coef_rank_stride;
 } chk_red_col;
 typedef struct chk_red_group {
     const int64_t* ids; int64_t n_keys; int64_t slots_per_rank; int32_t world; int32_t n_cols; int32_t single_row; int32_t pad_;

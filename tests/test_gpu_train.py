@@ -418,3 +418,116 @@ def test_claim_gather_rows_sends_each_row_once(dtype, width):
     ops.step_counter_bump(step)
     out3 = ops.claim_gather_rows(grad, rows, stamp, step)             # next step: claims are fresh
     assert torch.equal(summed(out3)[touched], ref[touched])
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("world", [1, 2])
+@pytest.mark.parametrize("rank,per_pair_q", [(33, False), (33, True), (257, False), (9, False), (129, True)])
+@pytest.mark.parametrize("mode", ["adagrad", "dense"])
+def test_reduce_apply_pair_coef_bit_identical_to_stored_rows(dtype, world, rank, per_pair_q, mode):
+    """The computed source of chk_reduce_apply (query rows + the three pair scalars chk_score_gather_train leaves when it is
+    given pair_coef) against the stored-row source fed by the same kernel's grad_rows: identical bits in the parameters, the
+    Adagrad state / the dense gradient, for short segments, shared-memory-sorted long segments and a > 4096-slot segment, one
+    query per nt pairs and per-pair queries, and `world` ranks' buffers (rank-major slots with rank strides)."""
+    from complexhyperbolickge_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    r, w = rank, 2 * rank
+    N, B, nt = 300, 24, 200 if rank <= 33 else 40
+    if rank <= 33 and not per_pair_q:
+        nt = 230                                               # 24 x 230 = 5520 pairs: room for a > 4096-slot segment
+    P = B * nt
+    Bq = P if per_pair_q else B
+    S = Bq + P
+    table = (torch.randn(N, w, generator=g, dtype=torch.float64) * (0.5 / np.sqrt(w))).to(dtype).cuda()
+    bh, bt = torch.randn(N, generator=g, dtype=torch.float64).to(dtype).cuda(), torch.randn(N, generator=g, dtype=torch.float64).to(dtype).cuda()
+    hyper = torch.tensor([0.1, 1e-10, 1.0 / (world * P), float(B), 0, 0, 1.0 / (world * B), 0], dtype=torch.float64, device="cuda")
+    ids = torch.randint(0, N, (world, S), generator=g)
+    if rank <= 33 and not per_pair_q:
+        ids[:, Bq + 50:Bq + 50 + 4300] = 7                    # > SORT_CAP slots name one row (sorted in place in global memory)
+    ids[:, Bq + P - 400:Bq + P - 100] = 11                    # a shared-memory-sort segment
+    ids[:, :min(Bq, 5)] = 11                                  # ... that also receives stored (head) rows
+    ids = ids.cuda().contiguous()
+    o_row = Bq * w
+    L_rows = o_row + P * w + P
+    L_coef = o_row + Bq * w + P * 4 + P
+    flat_rows = torch.zeros(world, L_rows, dtype=dtype, device="cuda")
+    flat_coef = torch.zeros(world, L_coef, dtype=dtype, device="cuda")
+    for k in range(world):
+        q = (torch.randn(Bq, w, generator=g, dtype=torch.float64) * (0.6 / np.sqrt(w))).to(dtype).cuda()
+        g_ent = torch.randn(Bq, w, generator=g, dtype=torch.float64).to(dtype).cuda()
+        heads, tails = ids[k, :Bq].contiguous(), ids[k, Bq:].contiguous()
+        qs = (nt, 1) if per_pair_q else (1, 0)
+        outs = []
+        for coef_mode in (False, True):
+            lp, gs, gq = torch.zeros(B, dtype=dtype, device="cuda"), torch.zeros(B, nt, dtype=dtype, device="cuda"), torch.zeros(Bq, w, dtype=dtype, device="cuda")
+            rows = None if coef_mode else torch.zeros(P, w, dtype=dtype, device="cuda")
+            cf = torch.zeros(P, 4, dtype=dtype, device="cuda") if coef_mode else None
+            gbh = None if per_pair_q else torch.zeros(B, dtype=dtype, device="cuda")
+            ops.score_gather_train(r, B, nt, q, qs[0], qs[1], table, tails, heads, qs[0], qs[1], bh, bt, hyper, lp, gs, gq, rows, gbh,
+                                   pair_coef=cf)
+            outs.append((lp, gs, gq, rows, cf))
+        for x, y in zip(outs[0][:3], outs[1][:3]):
+            assert torch.equal(x, y)                           # the other outputs of K3 do not depend on the mode
+        flat_rows[k, :o_row] = g_ent.view(-1); flat_rows[k, o_row:o_row + P * w] = outs[0][3].view(-1); flat_rows[k, o_row + P * w:] = outs[0][1].view(-1)
+        flat_coef[k, :o_row] = g_ent.view(-1); flat_coef[k, o_row:2 * o_row] = q.view(-1)
+        flat_coef[k, 2 * o_row:2 * o_row + P * 4] = outs[1][4].view(-1); flat_coef[k, 2 * o_row + P * 4:] = outs[1][1].view(-1)
+    p0, s0 = table.clone(), torch.rand(N, w, generator=g, dtype=torch.float64).to(dtype).cuda()
+    pb0, sb0 = bt.clone().view(N, 1), torch.rand(N, 1, generator=g, dtype=torch.float64).to(dtype).cuda()
+    inplace = mode == "adagrad"
+    results = []
+    for coef_mode in (False, True):
+        param, ssum, pscal, sscal = p0.clone(), s0.clone(), pb0.clone(), sb0.clone()
+        dense, dense_s = torch.full((N, w), 9.0, dtype=dtype, device="cuda"), torch.full((N, 1), 9.0, dtype=dtype, device="cuda")
+        work = ops.group_workspace(N, world * S, "cuda")
+        if coef_mode:
+            f0, Lf = flat_coef[0], L_coef
+            ecol = dict(src=[(f0, 0, Bq, Lf), (f0[o_row:], Bq, S, Lf)], pair=(f0[2 * o_row:], 0 if per_pair_q else nt, Lf))
+            gs_src = (f0[2 * o_row + P * 4:], Bq, S, Lf)
+        else:
+            f0, Lf = flat_rows[0], L_rows
+            ecol = dict(src=[(f0, 0, Bq, Lf), (f0[o_row:], Bq, S, Lf)])
+            gs_src = (f0[o_row + P * w:], Bq, S, Lf)
+        cols = [dict(ecol, param=param, state0=ssum if inplace else None, dense=None if inplace else dense),
+                dict(param=pscal, state0=sscal if inplace else None, dense=None if inplace else dense_s, src=[gs_src])]
+        groups = [dict(ids=ids.view(-1), n_keys=N, slots_per_rank=S, world=world, work=work, cols=cols)]
+        ops.group_build(ids.view(-1), N, work)
+        ops.reduce_apply(param, ops.CHK_OPT_ADAGRAD if inplace else ops.CHK_OPT_NONE, groups, hyper)
+        ops.step_finish(param, [work], None, None, None)
+        torch.cuda.synchronize()
+        results.append((param, ssum, pscal, sscal, dense, dense_s))
+    for x, y in zip(*results):
+        assert torch.equal(x, y)
+    if inplace:
+        assert not torch.equal(results[0][0], p0) and torch.isfinite(results[0][0]).all()
+    else:
+        assert (results[0][4] != 9.0).any() and torch.isfinite(results[0][4]).all()
+
+
+@pytest.mark.parametrize("graph", [False, True])
+@pytest.mark.parametrize("name,rank,dtype,double_neg,opt_name", [
+    ("FFTRotH", 33, "float", False, "Adagrad"), ("FFTRefH", 33, "double", False, "Adam"), ("FFTAttH", 17, "float", True, "Adagrad"),
+    ("FFTRotH", 257, "float", False, "Adagrad"), ("FFTRotH", 65, "double", True, "Adagrad"), ("FFTRotH", 9, "float", False, "Adam")])
+def test_fused_step_pair_coef_equals_stored_rows(name, rank, dtype, double_neg, opt_name, graph):
+    """FusedKGOptimizer with the tail-row gradients rebuilt in the reduce (the default) and with stored rows (pair_coef=False):
+    identical bits in every parameter, the optimizer state and the loss after several steps with duplicates and long segments."""
+    from complexhyperbolickge_b200.optim import N3
+    from complexhyperbolickge_b200.train import FusedKGOptimizer
+    B, neg, steps, n_ent = 48, 40, 6, 90                     # 48 x 41 slots over 90 rows: most segments are long (> 32 slots)
+    g = torch.Generator().manual_seed(9)
+    ex = torch.stack([torch.randint(0, n_ent, (B * steps,), generator=g), torch.randint(0, 10, (B * steps,), generator=g),
+                      torch.randint(0, n_ent, (B * steps,), generator=g)], 1).cuda()
+    finals = []
+    for pc in (False, None):
+        m = _mk(name, rank, dtype, n_ent=n_ent)
+        mk = (lambda ps: torch.optim.Adagrad(ps, lr=0.05)) if opt_name == "Adagrad" else (lambda ps: torch.optim.Adam(ps, lr=1e-3))
+        opt = FusedKGOptimizer(m, N3(0.0), mk(m.parameters()), B, 1, neg, double_neg, verbose=False, seed=5, use_cuda_graph=graph,
+                               pair_coef=pc)
+        assert opt._plan(B).coef_mode == (pc is None)
+        for i in range(steps):
+            opt.fused_step(ex[i * B:(i + 1) * B])
+        key = "sum" if opt_name == "Adagrad" else "exp_avg_sq"
+        finals.append([p.detach().clone() for p in m.parameters()] + [opt.optimizer.state[p][key].clone() for p in m.parameters()] +
+                      [opt._loss_sum.clone()])
+    for x, y in zip(*finals):
+        assert torch.equal(x, y)
+    assert np.isfinite(finals[0][-1].item())

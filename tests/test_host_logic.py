@@ -23,7 +23,7 @@ def test_capi_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(L, name), f"{name} declared in include/chk_b200.h but not exported"
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
-    assert _lib.lib().chk_abi_version() == 3
+    assert _lib.lib().chk_abi_version() == 4
 
 
 def test_no_cpu_fallback():

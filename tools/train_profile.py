@@ -27,8 +27,9 @@ def main():
     mk = (lambda ps: torch.optim.Adagrad(ps, lr=lr)) if opt_name == "Adagrad" else (lambda ps: torch.optim.Adam(ps, lr=lr))
     ex = synthetic.train_examples(graph)
     batches = bench.cycle_batches(ex[torch.randperm(ex.shape[0], generator=torch.Generator().manual_seed(0))], 64, 500).to(dev)
+    pc = False if os.environ.get("CHK_PAIR_COEF") == "0" else None      # A/B: stored tail-gradient rows instead of pair coefficients
     for use_graph in (False, True):
-        opt = FusedKGOptimizer(model, N3(0.0), mk(model.parameters()), 500, 1, neg, dn, verbose=False, use_cuda_graph=use_graph)
+        opt = FusedKGOptimizer(model, N3(0.0), mk(model.parameters()), 500, 1, neg, dn, verbose=False, use_cuda_graph=use_graph, pair_coef=pc)
         n = steps if not use_graph else 60
         for i in range(3):
             opt.fused_step(batches[i])
@@ -40,7 +41,7 @@ def main():
             opt.fused_step(batches[(3 + i) % 64])
         e1.record()
         torch.cuda.synchronize()
-        print(f"{wl} graph={use_graph}: {e0.elapsed_time(e1) / n * 1e3:.1f} us/step (device), {(time.perf_counter() - t0) / n * 1e6:.1f} us/step (host)", flush=True)
+        print(f"{wl} pair_coef={pc is None} graph={use_graph}: {e0.elapsed_time(e1) / n * 1e3:.1f} us/step (device), {(time.perf_counter() - t0) / n * 1e6:.1f} us/step (host)", flush=True)
         if os.environ.get("CHK_PROFILE_EAGER_ONLY"):
             break
 
