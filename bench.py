@@ -502,10 +502,30 @@ def measure_train(model, graph, opt_name, lr, B, neg, double_neg, steps, warmup,
            "algorithmic_bytes_per_triple": bpt,
            "hbm_frac_per_gpu": (Bg / world) / (ms * 1e-3) * bpt / 1e9 / hbm,
            "path": ("FusedDataParallelKGOptimizer.step: fused chain per rank on rows rank::world (CUDA graph incl. NCCL), "
-                    + ("sparse row exchange: all_gather of slot ids + contribution rows, one-kernel ordered reduce + Adagrad in place"
+                    + ("sparse exchange: all_gather of slot ids + per-rank contributions (head-gradient rows, query rows, 16 B of pair "
+                       "coefficients per negative instead of its gradient row), one-kernel ordered reduce that rebuilds the rows + Adagrad in place"
+                       + ("; tables owner-sharded in symmetric memory: K3 reads tail rows from their owner over NVLink, each rank updates only its own rows"
+                          if getattr(opt, "owner_sharded", False) else "; every replica applies every update")
                        if getattr(opt, "sparse_entity", False) else "local segment-reduce into a flat dense gradient + ONE all_reduce + dense apply")
                     if world > 1 else
-                    "FusedKGOptimizer.fused_step: prep(sampler) -> K1 -> K3 fwd+loss+bwd -> K1 adjoint -> ordered segment-reduce + optimizer (CUDA graph)")}
+                    "FusedKGOptimizer.fused_step: prep(sampler) -> K1 -> K3 fwd+loss+bwd (pair coefficients) -> K1 adjoint -> ordered segment-reduce "
+                    "rebuilding the tail-row gradients + optimizer (CUDA graph)")}
+    if world > 1 and getattr(opt, "owner_sharded", False):
+        # owner-sharded tables: the replicas are made current once per epoch (epoch() does it); timed here on its own and
+        # amortised over the steps of one epoch of this synthetic graph
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dist.barrier()
+        s0.record()
+        opt.sync_replicas()
+        s1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([s0.elapsed_time(s1)], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        steps_per_epoch = max(1, ex.shape[0] // Bg)
+        out["owner_sharded"] = True
+        out["replica_sync_ms_per_epoch"] = t.item()
+        out["steps_per_epoch"] = steps_per_epoch
+        out["value_incl_epoch_sync"] = Bg / ((ms + t.item() / steps_per_epoch) * 1e-3)
     if world > 1 and getattr(opt, "sparse_entity", False):
         pl = opt._plan(opt.local_batch_size)
         nbytes = pl.flat.numel() * es + pl.ent_ids.numel() * 8
@@ -611,14 +631,16 @@ def kernel_rooflines(device, peaks):
         tails = torch.randint(0, n_ent, (B, nt), generator=g, device=device)
         hyper = torch.tensor([0.1, 1e-10, 1.0 / (B * nt), float(B), 0, 0, 1.0 / B, 0], dtype=torch.float64, device=device)
         lp, gs = torch.empty(B, device=device, dtype=f32), torch.empty(B, nt, device=device, dtype=f32)
-        gq, grow, gbh = torch.empty(B, 2 * rank, device=device, dtype=f32), torch.empty(B * nt, 2 * rank, device=device, dtype=f32), torch.empty(B, device=device, dtype=f32)
-        ms3 = _time_kernel(lambda: ops.score_gather_train(rank, B, nt, q, 1, 0, ent, tails, heads, 1, 0, bh, bt, hyper, lp, gs, gq, grow, gbh))
-        by3 = B * train_bytes_per_triple(rank, neg, 4)
+        gq, coef, gbh = torch.empty(B, 2 * rank, device=device, dtype=f32), torch.empty(B * nt, 4, device=device, dtype=f32), torch.empty(B, device=device, dtype=f32)
+        ms3 = _time_kernel(lambda: ops.score_gather_train(rank, B, nt, q, 1, 0, ent, tails, heads, 1, 0, bh, bt, hyper, lp, gs, gq, None, gbh,
+                                                          pair_coef=coef))
+        # per triple: (1+neg) gathered tail rows + per pair (tail id 8 B, bt 4 B, coefficients 16 B, d loss/d score 4 B) + the query row and its gradient
+        by3 = B * (nt * (2 * rank * 4 + 32) + 2 * 2 * rank * 4)
         out[key] = {"bound": "hbm", "achieved": by3 / ms3 / 1e6, "peak": hbm, "unit": "GB/s", "frac": by3 / ms3 / 1e6 / hbm, "traffic": None,
-                    "kernel": f"K3 training pass chk_score_gather_train (scores + loss + adjoint, tail rows gathered once), rank {rank} fp32, "
-                              f"B={B}, neg={neg}, 1M-entity table", "kernel_ms": ms3,
+                    "kernel": f"K3 training pass chk_score_gather_train (scores + loss + adjoint as pair coefficients, tail rows gathered once), "
+                              f"rank {rank} fp32, B={B}, neg={neg}, 1M-entity table", "kernel_ms": ms3,
                     "algorithmic_bytes_per_triple": by3 // B, "triples_per_launch": B, "peak_source": src}
-        del ent, bh, bt, q, tails, grow
+        del ent, bh, bt, q, tails, coef
     return out
 
 
@@ -763,7 +785,7 @@ def run_ours(args):
                 500, 100, False, 50, 5, device, pg, world, peaks)
             if line is not None and "error" not in line["train_big4m"]:
                 line["train_big4m"]["config"] = (f"BASELINE.json configs[4]: FFTRotH rank={rank} Adagrad, 500 triples per rank x{world}, neg=100, "
-                                                 "synthetic 4M-entity graph, replicated tables")
+                                                 "synthetic 4M-entity graph, " + ("owner-sharded tables (symmetric memory)" if line["train_big4m"].get("owner_sharded") else "replicated tables"))
     del model
     torch.cuda.empty_cache()
     if not args.no_train:

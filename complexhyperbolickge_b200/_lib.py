@@ -80,7 +80,10 @@ SIGNATURES = {
     "chk_train_prep": (_i, [_p, _i64, _i64, _i64, _i, _p, _p, ctypes.c_uint64, _p, ctypes.c_uint32, _p, _p, _p, _p]),
     "chk_score_gather_train": (_i, [_i, _i, _i64, _i64, _p, _i64, _i64, _p, _p, _p, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "chk_group_workspace_bytes": (_i64, [_i64, _i64]),
-    "chk_group_build": (_i, [_p, _i64, _i64, _p, _p]),
+    "chk_group_build": (_i, [_p, _i64, _i64, _i64, _i64, _p, _p]),
+    "chk_score_gather_train_peer": (_i, [_i, _i, _i64, _i64, _p, _i64, _i64, _p, _p, _i64, _i, _p, _p, _i64, _i64, _p, _p, _p, _p, _p, _p, _p,
+                                         _p, _p]),
+    "chk_peer_gather_rows": (_i, [_i, _p, _i64, _p, _i64, _i64, _p, _p]),
     "chk_reduce_apply": (_i, [_i, _i, ctypes.POINTER(RedGroup), _i, _p, _i, _p, _i64, _p, _p, _p]),
     "chk_step_finish": (_i, [_i, ctypes.POINTER(_p), _i, _p, _i64, _p, _p, _p]),
     "chk_dense_apply": (_i, [_i, _i, ctypes.POINTER(DenseTab), _i, _p, _p, _p]),

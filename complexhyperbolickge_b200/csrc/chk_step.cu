@@ -84,9 +84,12 @@ __host__ __device__ inline GroupView group_view(void* work, int64_t n_keys, int6
     return v;
 }
 
-__global__ void __launch_bounds__(256) group_count_kernel(const int64_t* __restrict__ ids, int64_t total, GroupView v) {
-    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x)
-        v.pos[g] = atomicAdd(v.count + ids[g], 1);
+// Slots whose row lies outside [own_lo, own_hi) are not grouped (pos = -1): the rank does not own the row (owner-sharded tables).
+__global__ void __launch_bounds__(256) group_count_kernel(const int64_t* __restrict__ ids, int64_t total, GroupView v, int64_t own_lo, int64_t own_hi) {
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t id = ids[g];
+        v.pos[g] = (id >= own_lo && id < own_hi) ? atomicAdd(v.count + id, 1) : -1;
+    }
 }
 // The slot that arrived first at a row (pos == 0) allocates the row's segment in `order` and appends the row to the list of
 // short segments (<= SHORT_MAX slots: one warp reduces them from registers) or, from the end of the same array, to the list of
@@ -127,6 +130,7 @@ __global__ void __launch_bounds__(256) group_order_kernel(const int64_t* __restr
     for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
         const int64_t id = ids[g];
         const int p = v.pos[g];
+        if (p < 0) continue;                     // not this rank's row
         v.order[v.base[id] + p] = (int)g;
         if (p == 0) v.count[id] = 0;             // nobody reads the count any more (the segment list carries the lengths): ready for the next step
     }
@@ -1055,13 +1059,13 @@ extern "C" int64_t chk_group_workspace_bytes(int64_t n_keys, int64_t total_slots
     return (int64_t)sizeof(int) * (4 + 2 * n_keys + 5 * total_slots);
 }
 
-extern "C" int chk_group_build(const int64_t* ids, int64_t total_slots, int64_t n_keys, void* work, void* stream) {
+extern "C" int chk_group_build(const int64_t* ids, int64_t total_slots, int64_t n_keys, int64_t own_lo, int64_t own_hi, void* work, void* stream) {
     if (total_slots == 0) return CHK_OK;
-    if (!ids || !work || chk_group_workspace_bytes(n_keys, total_slots) < 0) { chk_set_error("chk_group_build: bad argument"); return CHK_EINVAL; }
+    if (!ids || !work || chk_group_workspace_bytes(n_keys, total_slots) < 0 || own_lo < 0 || own_hi > n_keys) { chk_set_error("chk_group_build: bad argument"); return CHK_EINVAL; }
     cudaStream_t st = (cudaStream_t)stream;
     GroupView v = group_view(work, n_keys, total_slots);
     const int grid = grid_for(total_slots, 256, 148 * 8);
-    group_count_kernel<<<grid, 256, 0, st>>>(ids, total_slots, v);
+    group_count_kernel<<<grid, 256, 0, st>>>(ids, total_slots, v, own_lo, own_hi);
     group_alloc_kernel<<<grid, 256, 0, st>>>(ids, total_slots, v);
     group_order_kernel<<<grid, 256, 0, st>>>(ids, total_slots, v);
     CHK_CUDA_LAUNCH_CHECK("group kernels");

@@ -503,10 +503,31 @@ def group_workspace(n_keys, total_slots, device):
     return torch.zeros((nbytes // 4,), dtype=torch.int32, device=device)
 
 
-def group_build(ids, n_keys, work):
+def group_build(ids, n_keys, work, own=None):
+    """own = (lo, hi): group only the slots whose row lies in [lo, hi) (owner-sharded tables); None = every slot."""
     _chk(ids, work)
-    _lib.check(_lib.lib().chk_group_build(_p(ids), ids.numel(), n_keys, _p(work), _stream()), "chk_group_build")
+    lo, hi = (0, n_keys) if own is None else own
+    _lib.check(_lib.lib().chk_group_build(_p(ids), ids.numel(), n_keys, lo, hi, _p(work), _stream()), "chk_group_build")
     _launched(3)
+
+
+def score_gather_train_peer(rank, B, nt, q, q_stride_b, q_stride_j, peer_tables, peer_bt, rows_per_owner, tail_idx, head_idx,
+                            head_stride_b, head_stride_j, bh, hyper, loss_part, grad_scores, grad_q, grad_rows, g_bh, pair_coef=None):
+    """K3 training pass on owner-sharded tables: peer_tables / peer_bt are int64 device tensors of `world` base pointers."""
+    _chk(q, peer_tables, peer_bt, tail_idx, head_idx, bh, hyper, loss_part, grad_scores, grad_q, grad_rows, g_bh, pair_coef)
+    _lib.check(_lib.lib().chk_score_gather_train_peer(_dt(q), rank, B, nt, _p(q), q_stride_b, q_stride_j, _p(peer_tables), _p(peer_bt),
+                                                      rows_per_owner, peer_tables.numel(), _p(tail_idx), _p(head_idx), head_stride_b, head_stride_j, _p(bh),
+                                                      _p(hyper), _p(loss_part), _p(grad_scores), _p(grad_q), _p(grad_rows),
+                                                      _p(pair_coef), _p(g_bh), _stream()), "chk_score_gather_train_peer")
+    _launched(1)
+
+
+def peer_gather_rows(peer_tables, rows_per_owner, ids, width, out):
+    """out[i, :] = (table copy of the owner of row ids[i])[ids[i], :]."""
+    _chk(peer_tables, ids, out)
+    _lib.check(_lib.lib().chk_peer_gather_rows(_dt(out), _p(peer_tables), rows_per_owner, _p(ids), ids.numel(), width, _p(out),
+                                               _stream()), "chk_peer_gather_rows")
+    _launched(1)
 
 
 def _red_groups(groups):

@@ -146,13 +146,22 @@ class FusedDataParallelKGOptimizer(FusedKGOptimizer):
       contribution buffers (gradient rows per slot, duplicates not yet merged); then ONE kernel (chk_reduce_apply) walks
       the union of the touched rows, sums each row's contributions in (rank, slot) order — the same bits on every replica —
       and applies the row-sparse Adagrad update in place.  No dense N x 2r gradient exists, nothing is scattered back.
+      With NCCL the big tables are additionally **owner-sharded** (``owner_sharded``): every rank keeps a full-layout copy in
+      symmetric (peer-accessible) memory, but only the rows of its own block ``[rank * rows_per_owner, ...)`` are current.  K3 reads
+      every tail row from its owner's copy over NVLink (chk_score_gather_train_peer), the head rows are fetched the same way
+      (chk_peer_gather_rows), and each rank reduces and updates ONLY the rows it owns — the update work per rank no longer grows
+      with the number of ranks.  ``sync_replicas()`` (one in-place all_gather per table, called at the end of ``epoch()``) makes
+      every copy current again for evaluation / ``state_dict()``.  The two all_gathers of a step order the accesses: a rank reads
+      a peer's rows only after that peer finished the previous step's update, and updates its rows only after every peer's K3.
     * **dense all_reduce** (tables smaller than the rows that would travel: every table at FB15k-237 / WN18RR size, and the
       relation tables always): the local contributions are segment-reduced into dense gradients that are views of one flat
       buffer, ONE all_reduce sums it, chk_dense_apply runs torch.optim.Adagrad / Adam over the tables and clears it."""
 
-    def __init__(self, *args, process_group=None, sparse_exchange=None, **kw):
+    def __init__(self, *args, process_group=None, sparse_exchange=None, owner_sharded=None, **kw):
         """sparse_exchange: None = decide by size (below); True / False force the entity-keyed tables onto the sparse row
-        exchange / the dense all_reduce (tests and small-scale checks of the big-table path)."""
+        exchange / the dense all_reduce (tests and small-scale checks of the big-table path).  owner_sharded: None = shard the
+        update of the sparse tables by owner whenever that path exists (NCCL, world > 1, pair coefficients, no N3 / F2);
+        False = every replica applies every update."""
         super().__init__(*args, **kw)
         self.pg = process_group
         self.world = _world(process_group)
@@ -178,6 +187,59 @@ class FusedDataParallelKGOptimizer(FusedKGOptimizer):
             p.grad = flat[o:o + p.numel()].view_as(p)
             o += p.numel()
         self._flat_grad = flat
+        self.owner_sharded = False
+        self.own = None
+        can = (self.sparse_entity and self.world > 1 and self._reg is None and self._pair_coef_mode()
+               and dist.get_backend(self.pg) == "nccl")
+        if owner_sharded and not can:
+            raise ValueError("owner_sharded=True needs NCCL, world > 1, the sparse exchange, pair coefficients and no N3 / F2 regulariser")
+        if can and owner_sharded is not False:
+            self._setup_owner_shards()
+
+    # ------------------------------------------------------------------------------------------ owner-sharded tables
+    def _sparse_params(self):
+        m = self.model
+        return [("entity", m.entity.weight), ("bh", m.bh.weight), ("bt", m.bt.weight)]
+
+    def _setup_owner_shards(self):
+        """Moves entity / bh / bt into symmetric memory (padded to world * rows_per_owner rows so that the replica sync is an
+        in-place all_gather), pads their Adagrad state likewise, and builds the device arrays of peer base pointers."""
+        import torch.distributed._symmetric_memory as symm_mem
+        m, W, r = self.model, self.world, self.rank_id
+        N = m.sizes[0]
+        group = self.pg if self.pg is not None else dist.group.WORLD
+        rpo = (N + W - 1) // W
+        self.rows_per_owner = rpo
+        self.own = (min(r * rpo, N), min((r + 1) * rpo, N))
+        self._symm, self._state_pad = {}, {}
+        dev = m.entity.weight.device
+        for name, p in self._sparse_params():
+            buf = symm_mem.empty((rpo * W, p.shape[1]), dtype=p.dtype, device=dev)
+            hdl = symm_mem.rendezvous(buf, group)
+            buf.zero_()
+            buf[:N].copy_(p.data)
+            p.data = buf[:N]
+            self._symm[name] = (buf, hdl, torch.tensor(list(hdl.buffer_ptrs), dtype=torch.int64, device=dev))
+            st = self.optimizer.state[p]
+            pad = torch.zeros((rpo * W, p.shape[1]), dtype=st["sum"].dtype, device=dev)
+            pad[:N].copy_(st["sum"])
+            st["sum"] = pad[:N]
+            self._state_pad[name] = pad
+        torch.cuda.synchronize()
+        dist.barrier(group=self.pg)
+        self.owner_sharded = True
+        self.model.parameters_changed()
+
+    def sync_replicas(self):
+        """Owner-sharded tables: every rank receives the current rows (and Adagrad state) of the other owners.  Needed before
+        the parameters are read outside the training step (evaluation, state_dict, checkpoint); epoch() calls it."""
+        if not self.owner_sharded:
+            return
+        r, rpo = self.rank_id, self.rows_per_owner
+        for name, _ in self._sparse_params():
+            for t in (self._symm[name][0], self._state_pad[name]):
+                dist.all_gather_into_tensor(t.view(-1), t[r * rpo:(r + 1) * rpo].reshape(-1), group=self.pg)
+        self.model.parameters_changed()
 
     # ------------------------------------------------------------------------------------------ plan
     def _build_groups(self, pl):
@@ -201,6 +263,10 @@ class FusedDataParallelKGOptimizer(FusedKGOptimizer):
                 ecols.append(sp_col(m.bh.weight, (f0[off["gs" if pl.dn else "g_bh"]:], 0, Bq, L)))
                 ecols.append(sp_col(m.bt.weight, (f0[off["gs"]:], Bq, S_e, L)))
             groups = [dict(ids=pl.ent_group_ids, n_keys=N, slots_per_rank=S_e, world=W, work=pl.w_ent, cols=ecols)]
+            if self.owner_sharded:                       # local staging of the head rows / head biases fetched from their owners
+                pl.stage_ent = torch.zeros((Bq, m.entity.weight.shape[1]), dtype=pl.flat.dtype, device=ent_dev)
+                pl.stage_bh = torch.zeros((Bq,), dtype=pl.flat.dtype, device=ent_dev)
+                pl.arange_q = torch.arange(Bq, dtype=torch.int64, device=ent_dev)
         else:
             pl.w_ent = ops.group_workspace(N, S_e, dev)
             pl.ent_group_ids, pl.ent_group_slots = pl.ent_ids, S_e
@@ -213,6 +279,8 @@ class FusedDataParallelKGOptimizer(FusedKGOptimizer):
         groups += self._relation_groups(pl, dense_col)
         pl.groups = groups
         pl.red = ops._red_groups(groups)
+        if self.sparse_entity:                           # two launches: the relation tables' all_reduce runs beside the entity reduce
+            pl.red_ent, pl.red_rel = ops._red_groups(groups[:1]), ops._red_groups(groups[1:])
         pl.works = [pl.w_ent, pl.w_rel]
 
     def _graph_batch(self):
@@ -227,7 +295,29 @@ class FusedDataParallelKGOptimizer(FusedKGOptimizer):
             dist.all_gather_into_tensor(pl.all_ids.view(-1), pl.ent_ids, group=self.pg)
         elif self.sparse_entity:
             pl.all_ids.view(-1).copy_(pl.ent_ids)
-        super()._after_prep(pl)
+        cur = torch.cuda.current_stream()
+        self._side.wait_stream(cur)
+        with torch.cuda.stream(self._side):                 # owner-sharded: only the slots naming this rank's rows are grouped
+            ops.group_build(pl.ent_group_ids, self.model.sizes[0], pl.w_ent, own=self.own)
+            ops.group_build(pl.rels_b, self.model.rel.weight.shape[0], pl.w_rel)
+
+    def _head_tables(self, pl, learn):
+        if not self.owner_sharded:
+            return super()._head_tables(pl, learn)
+        rpo = self.rows_per_owner
+        ops.peer_gather_rows(self._symm["entity"][2], rpo, pl.heads, pl.stage_ent.shape[1], pl.stage_ent)
+        if learn:
+            ops.peer_gather_rows(self._symm["bh"][2], rpo, pl.heads, 1, pl.stage_bh)
+        return pl.stage_ent, pl.arange_q, (pl.stage_bh if learn else None)
+
+    def _score_train(self, pl, head_ix, bh_tab, learn):
+        if not self.owner_sharded:
+            return super()._score_train(pl, head_ix, bh_tab, learn)
+        m = self.model
+        qsb, qsj = (pl.nt, 1) if pl.dn else (1, 0)
+        ops.score_gather_train_peer(m.rank, pl.B, pl.nt, pl.q, qsb, qsj, self._symm["entity"][2], self._symm["bt"][2] if learn else None,
+                                    self.rows_per_owner, pl.tails, head_ix, qsb, qsj, bh_tab, self._hyper, pl.loss_part, pl.gs,
+                                    pl.grad_q, pl.grow, pl.g_bh if learn else None, pair_coef=pl.coef)
 
     def _apply(self, pl):
         m, st = self.model, self.optimizer.state
@@ -237,12 +327,22 @@ class FusedDataParallelKGOptimizer(FusedKGOptimizer):
                 dist.all_gather_into_tensor(pl.all_flat.view(-1), pl.flat, group=self.pg)
             else:
                 pl.all_flat.view(-1).copy_(pl.flat)
-        torch.cuda.current_stream().wait_stream(self._side)
-        # one launch: entity-keyed rows of all ranks summed in (rank, slot) order + Adagrad in place (sparse exchange) and / or
-        # the local row sums written into the dense gradients
-        ops.reduce_apply(m.entity.weight, ops.CHK_OPT_ADAGRAD if self.sparse_entity else ops.CHK_OPT_NONE, pl.red, self._hyper)
-        if W > 1:
-            dist.all_reduce(self._flat_grad, op=dist.ReduceOp.SUM, group=self.pg)
+        cur = torch.cuda.current_stream()
+        cur.wait_stream(self._side)
+        if self.sparse_entity and W > 1:
+            # relation tables: local row sums into the dense gradients, then their all_reduce on the side stream WHILE the main
+            # stream sums the entity-keyed rows of all ranks in (rank, slot) order and applies Adagrad in place
+            ops.reduce_apply(m.entity.weight, ops.CHK_OPT_NONE, pl.red_rel, self._hyper)
+            self._side.wait_stream(cur)
+            with torch.cuda.stream(self._side):
+                dist.all_reduce(self._flat_grad, op=dist.ReduceOp.SUM, group=self.pg)
+            ops.reduce_apply(m.entity.weight, ops.CHK_OPT_ADAGRAD, pl.red_ent, self._hyper)
+            cur.wait_stream(self._side)
+        else:
+            # one launch: the local row sums written into the dense gradients (and, single rank, the sparse tables updated in place)
+            ops.reduce_apply(m.entity.weight, ops.CHK_OPT_ADAGRAD if self.sparse_entity else ops.CHK_OPT_NONE, pl.red, self._hyper)
+            if W > 1:
+                dist.all_reduce(self._flat_grad, op=dist.ReduceOp.SUM, group=self.pg)
         if self.kind == "adam":
             tabs = [(p.data, p.grad, st[p]["exp_avg"], st[p]["exp_avg_sq"]) for p in self._dense]
         else:
@@ -281,4 +381,5 @@ class FusedDataParallelKGOptimizer(FusedKGOptimizer):
         if self.world > 1:
             dist.all_reduce(total, op=dist.ReduceOp.SUM, group=self.pg)
         self.sync_optimizer_state()
+        self.sync_replicas()
         return total.item() / max(nb, 1)

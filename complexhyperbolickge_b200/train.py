@@ -258,12 +258,10 @@ class FusedKGOptimizer(KGOptimizer):
         if pl.dn:
             pl.rels_b.copy_(pl.batch[:, 1])
         self._after_prep(pl)
-        ops.query_fwd(m.KIND, r, bool(m.multi_c), ent, rel, rd, ctx, cw, pl.heads, pl.rels, out=(pl.q, pl.c_out))
-        qsb, qsj = (nt, 1) if pl.dn else (1, 0)
-        ops.score_gather_train(r, B, nt, pl.q, qsb, qsj, ent, pl.tails, pl.heads if learn else None, qsb, qsj,
-                               m.bh.weight.data.view(-1) if learn else None, m.bt.weight.data.view(-1) if learn else None,
-                               self._hyper, pl.loss_part, pl.gs, pl.grad_q, pl.grow, pl.g_bh if learn else None, pair_coef=pl.coef)
-        ops.query_bwd_into(m.KIND, r, bool(m.multi_c), ent, rel, rd, ctx, cw, pl.heads, pl.rels, pl.grad_q, pl.g_ent, pl.g_rel,
+        ent_h, head_ix, bh_tab = self._head_tables(pl, learn)           # where K1 / K3 find the head rows and head biases
+        ops.query_fwd(m.KIND, r, bool(m.multi_c), ent_h, rel, rd, ctx, cw, head_ix, pl.rels, out=(pl.q, pl.c_out))
+        self._score_train(pl, head_ix if learn else None, bh_tab, learn)
+        ops.query_bwd_into(m.KIND, r, bool(m.multi_c), ent_h, rel, rd, ctx, cw, head_ix, pl.rels, pl.grad_q, pl.g_ent, pl.g_rel,
                            pl.g_rd, pl.g_ctx, pl.g_c)
         if pl.dn:
             ops.rowsum_groups(pl.g_rel, B, nt, pl.g_rel.shape[1], pl.s_rel)
@@ -276,6 +274,19 @@ class FusedKGOptimizer(KGOptimizer):
             hs = nt if pl.dn else 1
             ops.reg_factors(power, w, self._hyper, B, ent, rel, pl.heads, hs, pl.rels, pl.tails, nt, pl.g_ent, hs * 2 * r,
                             pl.s_rel, pl.s_rel.shape[1], pl.grow, nt * 2 * r, pl.loss_part)
+
+    def _head_tables(self, pl, learn):
+        """(entity table, head index, bh table) through which K1, its adjoint and K3 read the head rows / head biases."""
+        m = self.model
+        return m.entity.weight.data, pl.heads, (m.bh.weight.data.view(-1) if learn else None)
+
+    def _score_train(self, pl, head_ix, bh_tab, learn):
+        """K3 training pass on the step's (B, 1+neg) tails."""
+        m = self.model
+        qsb, qsj = (pl.nt, 1) if pl.dn else (1, 0)
+        ops.score_gather_train(m.rank, pl.B, pl.nt, pl.q, qsb, qsj, m.entity.weight.data, pl.tails, head_ix, qsb, qsj, bh_tab,
+                               m.bt.weight.data.view(-1) if learn else None, self._hyper, pl.loss_part, pl.gs, pl.grad_q, pl.grow,
+                               pl.g_bh if learn else None, pair_coef=pl.coef)
 
     def _after_prep(self, pl):
         """Ids are known: group the slots by row beside the forward / backward kernels (second stream)."""

@@ -174,11 +174,29 @@ int chk_score_gather_train(int dtype, int rank, int64_t B, int64_t nt,
                            void* loss_part, void* grad_scores, void* grad_q, void* grad_rows, void* pair_coef, void* g_bh,
                            void* stream);
 
+/* Owner-sharded tables (data parallel; no reference counterpart — optimizers/kg_optimizer.py:51 is single-device): every rank
+ * holds a full-layout copy of the entity / bt tables in peer-accessible (symmetric) memory, but only the rows it OWNS
+ * (row / rows_per_owner == rank) are current.  chk_score_gather_train_peer reads every tail row and bt value from its owner's
+ * copy over NVLink (peer_tables / peer_bt: device arrays of `world` <= 32 base pointers); chk_peer_gather_rows copies the rows `ids`
+ * of such a table into a local buffer (head rows for K1 and its adjoint, head biases).  bh: local [B]-indexable values. */
+int chk_score_gather_train_peer(int dtype, int rank, int64_t B, int64_t nt,
+                                const void* q, int64_t q_stride_b, int64_t q_stride_j,
+                                const void* const* peer_tables, const void* const* peer_bt, int64_t rows_per_owner, int world,
+                                const int64_t* tail_idx,
+                                const int64_t* head_idx, int64_t head_stride_b, int64_t head_stride_j,
+                                const void* bh, const double* hyper,
+                                void* loss_part, void* grad_scores, void* grad_q, void* grad_rows, void* pair_coef, void* g_bh,
+                                void* stream);
+int chk_peer_gather_rows(int dtype, const void* const* peer_tables, int64_t rows_per_owner, const int64_t* ids, int64_t n,
+                         int64_t width, void* out, void* stream);
+
 /* Grouping of `total_slots` slots by the table row they name (ids[s] in [0, n_keys)): fills the workspace (int32, size
  * chk_group_workspace_bytes, zero-initialised once by the caller; chk_reduce_apply / chk_step_finish leave it ready for
- * the next step) with per-row counts, segment bases, the slot order and the list of touched rows. */
+ * the next step) with per-row counts, segment bases, the slot order and the list of touched rows.  Only slots whose row lies in
+ * [own_lo, own_hi) are grouped (0, n_keys: all; an owner-sharded table: the rank's own row block) — chk_reduce_apply then
+ * touches nothing else. */
 int64_t chk_group_workspace_bytes(int64_t n_keys, int64_t total_slots);
-int chk_group_build(const int64_t* ids, int64_t total_slots, int64_t n_keys, void* work, void* stream);
+int chk_group_build(const int64_t* ids, int64_t total_slots, int64_t n_keys, int64_t own_lo, int64_t own_hi, void* work, void* stream);
 
 /* Segment-reduce + apply.  A group = one key space (entity ids; relation ids) with world*slots_per_rank slots numbered
  * rank-major (slot = k*slots_per_rank + s); a column = one table fed by up to two contribution sources: local slot s in

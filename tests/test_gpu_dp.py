@@ -45,7 +45,8 @@ def _examples(n_ent, n):
                         torch.randint(0, n_ent, (n,), generator=g)], 1)
 
 
-def _worker(rank, world, port, backend, sparse, opt_name, q):
+def _worker(rank, world, port, backend, mode, opt_name, q):
+    sparse = mode != "dense"
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     ngpu = torch.cuda.device_count()
     torch.cuda.set_device(rank % ngpu)
@@ -61,8 +62,9 @@ def _worker(rank, world, port, backend, sparse, opt_name, q):
             def get_neg_samples(self, b):
                 return _hash_negs(b, neg, n_ent)
         opt = Fed(m, N3(0.0), mk(m.parameters()), Bg, 1, neg, False, verbose=False, process_group=None, sparse_exchange=sparse,
-                  use_cuda_graph=(backend == "nccl"))
+                  owner_sharded=None if mode == "owner" else False, use_cuda_graph=(backend == "nccl"))
         assert opt.world == world and opt.local_batch_size == 23
+        assert opt.owner_sharded == (mode == "owner" and backend == "nccl")      # NCCL: peer-memory tables, update sharded by owner
         ex = _examples(n_ent, 230)
         torch.manual_seed(21 + rank)                      # ranks shuffle differently: rank 0's permutation must win
         losses = [opt.epoch(ex), opt.epoch(ex)]
@@ -95,9 +97,12 @@ def _worker(rank, world, port, backend, sparse, opt_name, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("sparse", [True, False])
+@pytest.mark.parametrize("mode", ["owner", "sparse", "dense"])
 @pytest.mark.parametrize("opt_name", ["Adagrad", "Adam"])
-def test_dp_epoch_equals_single_gpu_epoch(sparse, opt_name):
+def test_dp_epoch_equals_single_gpu_epoch(mode, opt_name):
+    """mode: owner = sparse exchange with owner-sharded tables in symmetric memory (NCCL only; under gloo it is the replicated
+    sparse exchange), sparse = every replica applies every update, dense = dense all_reduce of the gradients."""
+    sparse = mode != "dense"
     from complexhyperbolickge_b200.optim import N3
     from complexhyperbolickge_b200.train import FusedKGOptimizer
     if sparse and opt_name == "Adam":
@@ -106,7 +111,7 @@ def test_dp_epoch_equals_single_gpu_epoch(sparse, opt_name):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, backend, sparse, opt_name, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, backend, mode, opt_name, q)) for r in range(2)]
     for p in procs:
         p.start()
     try:

@@ -92,11 +92,14 @@ def main():
             def get_neg_samples(self, input_batch):
                 return self._negs_static
 
-        for sparse in (None, True):              # None: dense all_reduce of the small tables; True: sparse row exchange (big-table path)
+        # dense all_reduce of the small tables; sparse exchange with every replica applying every update; sparse exchange with
+        # owner-sharded tables in symmetric memory (the big-table path under NCCL)
+        for sparse, owner, tag in ((None, False, "dense"), (True, False, "sparse rows"), (True, None, "owner-sharded")):
             ref.load_state_dict(model.state_dict())
             f1 = FixedF(ref, N3(0.0), torch.optim.Adagrad(ref.parameters(), lr=0.05), B, 1, neg, False, verbose=False)
             f2 = FixedFDP(model, N3(0.0), torch.optim.Adagrad(model.parameters(), lr=0.05), B, 1, neg, False, verbose=False,
-                          process_group=dist.group.WORLD, sparse_exchange=sparse)
+                          process_group=dist.group.WORLD, sparse_exchange=sparse, owner_sharded=owner)
+            assert f2.owner_sharded == (tag == "owner-sharded")
             f1._negs_static = torch.zeros(B, neg, dtype=torch.int64, device=dev)
             f2._negs_static = torch.zeros(B // world, neg, dtype=torch.int64, device=dev)
             for it in range(4):
@@ -110,6 +113,7 @@ def main():
                 f2._negs_static.copy_(negs[rank::world])
                 f1.fused_step(batch)
                 f2.step(batch)
+            f2.sync_replicas()                                     # owner-sharded: every copy current again
             worst, replica = 0.0, 0.0
             for (k, a), (_, b) in zip(ref.named_parameters(), model.named_parameters()):
                 worst = max(worst, (a.detach() - b.detach()).abs().max().item() / max(a.detach().abs().max().item(), 1e-30))
@@ -120,7 +124,7 @@ def main():
             lsum = f2._loss_sum.clone().double()
             dist.all_reduce(lsum)
             if rank == 0:
-                print(f"[fused dp {name} r={r} {dtype} x{world} {'sparse rows' if sparse else 'dense'}] 4 steps: loss single "
+                print(f"[fused dp {name} r={r} {dtype} x{world} {tag}] 4 steps: loss single "
                       f"{f1._loss_sum.item() / 4:.9f} sum-over-ranks {lsum.item() / 4:.9f}  max |param diff| / max|param| = "
                       f"{worst:.2e}  max replica divergence = {replica:.1e}", flush=True)
             assert abs(f1._loss_sum.item() - lsum.item()) / 4 < (1e-10 if dtype == "double" else 1e-4)
