@@ -17,6 +17,9 @@
 //   chk_rowsum_groups   out[b,:] = sum_j in[b,j,:] in ascending j (double_neg: per-pair relation-row gradients).
 #include <cstdlib>
 #include "chk_common.cuh"
+#ifndef CHK_COEF_ONEPASS
+#define CHK_COEF_ONEPASS 1     // fp32 wide rows with pair coefficients: the whole row in ONE pass at 2 CTAs per SM and 128 registers (r2: 140 -> 126 us
+#endif                         // at the 4M-entity config; two passes of 5 + 4 chunks at 80 registers spilled and broadcast the descriptors twice)
 
 namespace {
 
@@ -674,7 +677,7 @@ __device__ __forceinline__ void coef_entity_phase1(const RGroup<T>& G, T lr, T e
             }
         }
         const int64_t rowoff = (int64_t)id * (2 * R);
-        if constexpr (NCH <= 5) coef_pass<T, R, 0, (NCH <= 5 ? NCH : 1)>(param, st, dense, rowoff, len, lane, dp, d1, d2, d3, pairmask, lr, eps);
+        if constexpr (NCH <= 5 || (CHK_COEF_ONEPASS && sizeof(T) == 4)) coef_pass<T, R, 0, NCH>(param, st, dense, rowoff, len, lane, dp, d1, d2, d3, pairmask, lr, eps);
         else {
             coef_pass<T, R, 0, 5>(param, st, dense, rowoff, len, lane, dp, d1, d2, d3, pairmask, lr, eps);
             coef_pass<T, R, 5, (NCH > 5 ? NCH - 5 : 1)>(param, st, dense, rowoff, len, lane, dp, d1, d2, d3, pairmask, lr, eps);
@@ -744,7 +747,7 @@ __device__ __forceinline__ void coef_long_segment(const RGroup<T>& G, int id, in
 }
 
 template <typename T, int W2, bool COEF>
-__global__ void __launch_bounds__(RWARPS * 32, (W2 > 0 && W2 <= 65) || W2 == 0 ? 4 : 3) reduce_apply_kernel(const RArgsStep<T> A) {
+__global__ void __launch_bounds__(RWARPS * 32, (W2 > 0 && W2 <= 65) || W2 == 0 ? 4 : ((CHK_COEF_ONEPASS && COEF && sizeof(T) == 4) ? 2 : 3)) reduce_apply_kernel(const RArgsStep<T> A) {
     using V = typename V2<T>::type;
     constexpr int MAXCH = 2;
     __shared__ int sbuf[SORT_CAP];
@@ -1122,7 +1125,8 @@ static int reduce_apply_t(int opt, const chk_red_group* groups, int n_groups, co
     if (coef && !(w2 == 9 || w2 == 17 || w2 == 33 || w2 == 65 || w2 == 129 || w2 == 257)) {
         chk_set_error("chk_reduce_apply: pair_coef needs the entity-group shape and a rank in {9,17,33,65,129,257}"); return CHK_EINVAL;
     }
-    const int grid4 = grid_for(max_seg, RWARPS, 148 * 4), grid3 = grid_for(max_seg, RWARPS, 148 * 3);
+    const int grid4 = grid_for(max_seg, RWARPS, 148 * 4);
+    const int grid3 = grid_for(max_seg, RWARPS, 148 * ((CHK_COEF_ONEPASS && coef && sizeof(T) == 4) ? 2 : 3));   // one resident wave
 #define CHK_RED_LAUNCH(W, G)                                                                                   \
     case W: if (coef) reduce_apply_kernel<T, W, true><<<G, RWARPS * 32, 0, st>>>(A);                          \
             else reduce_apply_kernel<T, W, false><<<G, RWARPS * 32, 0, st>>>(A);                              \
