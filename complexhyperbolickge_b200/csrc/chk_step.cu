@@ -19,7 +19,10 @@
 #include "chk_common.cuh"
 #ifndef CHK_COEF_ONEPASS
 #define CHK_COEF_ONEPASS 1     // fp32 wide rows with pair coefficients: the whole row in ONE pass at 2 CTAs per SM and 128 registers (r2: 140 -> 126 us
-#endif                         // at the 4M-entity config; two passes of 5 + 4 chunks at 80 registers spilled and broadcast the descriptors twice)
+#endif                         // at the 4M-entity config; two passes of 5 + 4 chunks at 80 registers spilled and broadcast the descriptors twice).
+// Tried and dropped in r2 (measured, no gain): prefetching the next segment's parameter / state rows to shared memory with
+// cp.async (129 us), computing the next segment's descriptors one iteration ahead (177 us: spills).  The kernel moves 428 MB of
+// random 2 KB rows read-modify-write at 3.4 TB/s (ncu: profiles/r2_final_train_big4m_raw.csv); a streaming copy reaches 6.5.
 
 namespace {
 
@@ -993,15 +996,36 @@ __global__ void __launch_bounds__(256) dense_apply_kernel(DList L, const double*
     }
 }
 
+// out[b, c] = sum_j in[b, j, c].  One CTA per (b, 32-column chunk): warp w adds the rows j = w, w + 8, ... (each a coalesced
+// 128-byte read, four in flight), the eight partial sums are combined in warp order — a fixed order, so the result is
+// bit-reproducible.  (r2: the first version ran one thread per (b, c) over all j serially: 20 us per table at B = 500,
+// nt = 101 — three of them were a fifth of the double_neg step.)
 template <typename T>
 __global__ void __launch_bounds__(256) rowsum_groups_kernel(const T* __restrict__ in, int64_t B, int64_t nj, int64_t width, T* __restrict__ out) {
-    const int64_t total = B * width;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t b = i / width, c = i - b * width;
+    __shared__ T part[8][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t chunks = (width + 31) / 32;
+    for (int64_t item = blockIdx.x; item < B * chunks; item += gridDim.x) {
+        const int64_t b = item / chunks, c = (item - b * chunks) * 32 + lane;
+        const bool on = c < width;
         const T* p = in + b * nj * width + c;
         T acc = T(0);
-        for (int64_t j = 0; j < nj; ++j) acc += p[j * width];
-        out[i] = acc;
+        int64_t j = warp;
+        for (; j + 24 < nj; j += 32) {
+            T v0 = T(0), v1 = T(0), v2 = T(0), v3 = T(0);
+            if (on) { v0 = p[j * width]; v1 = p[(j + 8) * width]; v2 = p[(j + 16) * width]; v3 = p[(j + 24) * width]; }
+            acc += v0; acc += v1; acc += v2; acc += v3;
+        }
+        for (; j < nj; j += 8) if (on) acc += p[j * width];
+        __syncthreads();                                               // part of the previous item has been read
+        part[warp][lane] = acc;
+        __syncthreads();
+        if (warp == 0 && on) {
+            T s = part[0][lane];
+#pragma unroll
+            for (int w = 1; w < 8; ++w) s += part[w][lane];
+            out[b * width + c] = s;
+        }
     }
 }
 
@@ -1189,7 +1213,7 @@ extern "C" int chk_rowsum_groups(int dtype, const void* in, int64_t B, int64_t n
     if (B == 0 || width == 0) return CHK_OK;
     if (B < 0 || nj < 1 || width < 0 || !in || !out) { chk_set_error("chk_rowsum_groups: bad argument"); return CHK_EINVAL; }
     cudaStream_t st = (cudaStream_t)stream;
-    const int grid = grid_for(B * width, 256, 148 * 8);
+    const int grid = grid_for(B * ((width + 31) / 32), 1, 148 * 8);
     if (dtype == CHK_F32) rowsum_groups_kernel<float><<<grid, 256, 0, st>>>((const float*)in, B, nj, width, (float*)out);
     else if (dtype == CHK_F64) rowsum_groups_kernel<double><<<grid, 256, 0, st>>>((const double*)in, B, nj, width, (double*)out);
     else { chk_set_error("unknown dtype %d", dtype); return CHK_EINVAL; }

@@ -233,7 +233,8 @@ int chk_step_finish(int dtype, void* const* group_works, int n_groups, const voi
  * whole tables from a dense gradient, which is cleared (run.py:205 hands the dense tables to torch.optim). */
 typedef struct chk_dense_tab { void* param; void* grad; void* state0; void* state1; int64_t n; } chk_dense_tab;
 int chk_dense_apply(int dtype, int opt, const chk_dense_tab* tabs, int n_tables, const double* hyper, const int32_t* step_id, void* stream);
-/* out[b,:] = sum_j in[b,j,:] in ascending j (double_neg: the nt per-pair relation-row gradients of a triple share a row). */
+/* out[b,:] = sum_j in[b,j,:] in a fixed order — eight interleaved partial sums (j mod 8), added in ascending order — so the
+ * result is bit-reproducible (double_neg: the nt per-pair relation-row gradients of a triple share a row). */
 int chk_rowsum_groups(int dtype, const void* in, int64_t B, int64_t nj, int64_t width, void* out, void* stream);
 /* N3 (power 3) / F2 (power 2) of the positive call's factors entity[h], rel[r], entity[t] (optimizers/regularizers.py:21-58):
  * value weight*sum|f|^p*hyper[6] added to loss_part[b], gradient rows added to the three contribution rows of triple b. */

@@ -531,3 +531,21 @@ def test_fused_step_pair_coef_equals_stored_rows(name, rank, dtype, double_neg, 
     for x, y in zip(*finals):
         assert torch.equal(x, y)
     assert np.isfinite(finals[0][-1].item())
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("B,nj,width", [(37, 101, 128), (5, 7, 1), (16, 251, 66), (3, 1, 33), (500, 101, 64)])
+def test_rowsum_groups_matches_torch(dtype, B, nj, width):
+    """chk_rowsum_groups (double_neg: per-pair relation-row gradients summed per triple) against torch.sum, twice (bit-reproducible)."""
+    from complexhyperbolickge_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(B, nj, width, generator=g, dtype=torch.float64).to(dtype).cuda()
+    outs = []
+    for _ in range(2):
+        out = torch.full((B, width), 7.0, dtype=dtype, device="cuda")
+        ops.rowsum_groups(x, B, nj, width, out)
+        outs.append(out)
+    assert torch.equal(outs[0], outs[1])
+    want = x.double().sum(1)
+    tol = 1e-13 if dtype == torch.float64 else 2e-6
+    assert (outs[0].double() - want).abs().max().item() <= tol * max(1.0, want.abs().max().item()) * (nj ** 0.5)
