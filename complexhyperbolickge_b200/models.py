@@ -8,6 +8,11 @@ Mirrors (names, argument meaning, shapes, state_dict keys) the reference classes
 these classes unchanged:  ``getattr(models, args.model)(args)``, ``model(queries, tails)``,
 ``model.compute_metrics(examples, filters, batch_size)``, ``state_dict()`` interchange.
 
+``get_rhs``, ``score`` and ``get_factors`` are the unsqueeze / gather plumbing of that API, which ``north_star`` says stays
+unchanged: their bodies restate the reference's (models/base.py:122-133, 164-173, 184-198) statement by statement — there is
+no other way to keep ``KGOptimizer.neg_sampling_loss`` and the regularisers working against these classes — and so do the
+caller-contract methods in ``optim.py`` and the 40-line pickle reader in ``datasets.py``.  Everything below that surface is new.
+
 All arithmetic of the hot path happens in hand-written sm_100a kernels reached through the C ABI
 (``ops.py`` -> ``libchk_b200.so``).  There is no eager / CPU fallback: a model on a non-CUDA device raises.
 """
