@@ -549,3 +549,99 @@ def test_rowsum_groups_matches_torch(dtype, B, nj, width):
     want = x.double().sum(1)
     tol = 1e-13 if dtype == torch.float64 else 2e-6
     assert (outs[0].double() - want).abs().max().item() <= tol * max(1.0, want.abs().max().item()) * (nj ** 0.5)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("rank,nt", [(33, 251), (257, 101), (65, 40), (257, 5)])
+@pytest.mark.parametrize("per_pair_q", [False, True])
+def test_score_gather_train_peer_equals_local(dtype, rank, nt, per_pair_q):
+    """Owner-sharded tables emulated on one GPU: three full-layout copies of the entity / bt tables in which only the rows a
+    copy OWNS are valid (the others are NaN).  chk_score_gather_train_peer (every tail row read from its owner's copy; the
+    cp.async row ring at rank 257 fp32) must give the bits of chk_score_gather_train on the plain table, and
+    chk_peer_gather_rows the rows index_select gives."""
+    from complexhyperbolickge_b200 import ops
+    g = torch.Generator().manual_seed(13)
+    r, w, world = rank, 2 * rank, 3
+    N, B = 1000, 37
+    rpo = (N + world - 1) // world
+    P, Bq = B * nt, (B * nt if per_pair_q else B)
+    table = (torch.randn(N, w, generator=g, dtype=torch.float64) * (0.5 / np.sqrt(w))).to(dtype).cuda()
+    bt = torch.randn(N, generator=g, dtype=torch.float64).to(dtype).cuda()
+    bh_vals = torch.randn(Bq, generator=g, dtype=torch.float64).to(dtype).cuda()          # head biases, already gathered
+    owner = torch.arange(N, device="cuda") // rpo
+    copies, bt_copies = [], []
+    for k in range(world):
+        t, b_ = table.clone(), bt.clone()
+        t[owner != k] = float("nan")
+        b_[owner != k] = float("nan")
+        copies.append(t); bt_copies.append(b_)
+    ptr_t = torch.tensor([t.data_ptr() for t in copies], dtype=torch.int64, device="cuda")
+    ptr_b = torch.tensor([t.data_ptr() for t in bt_copies], dtype=torch.int64, device="cuda")
+    q = (torch.randn(Bq, w, generator=g, dtype=torch.float64) * (0.6 / np.sqrt(w))).to(dtype).cuda()
+    tails = torch.randint(0, N, (B, nt), generator=g).cuda()
+    head_ix = torch.arange(Bq, device="cuda")
+    hyper = torch.tensor([0.1, 1e-10, 1.0 / P, float(B - 2), 0, 0, 1.0 / B, 0], dtype=torch.float64, device="cuda")   # two padding rows
+    qs = (nt, 1) if per_pair_q else (1, 0)
+    outs = []
+    for peer in (False, True):
+        lp, gs, gq = torch.zeros(B, dtype=dtype, device="cuda"), torch.zeros(B, nt, dtype=dtype, device="cuda"), torch.zeros(Bq, w, dtype=dtype, device="cuda")
+        cf = torch.zeros(P, 4, dtype=dtype, device="cuda")
+        gbh = None if per_pair_q else torch.zeros(B, dtype=dtype, device="cuda")
+        if peer:
+            ops.score_gather_train_peer(r, B, nt, q, qs[0], qs[1], ptr_t, ptr_b, rpo, tails, head_ix, qs[0], qs[1], bh_vals, hyper, lp, gs, gq,
+                                        None, gbh, pair_coef=cf)
+        else:
+            ops.score_gather_train(r, B, nt, q, qs[0], qs[1], table, tails, head_ix, qs[0], qs[1], bh_vals, bt, hyper, lp, gs, gq, None, gbh,
+                                   pair_coef=cf)
+        torch.cuda.synchronize()
+        outs.append((lp, gs, gq, cf) + (() if gbh is None else (gbh,)))
+    for x, y in zip(*outs):
+        assert torch.isfinite(x).all()
+        assert torch.equal(x, y)
+    assert outs[0][0].abs().sum().item() > 0
+    ids = torch.randint(0, N, (77,), generator=g).cuda()
+    got = torch.zeros(77, w, dtype=dtype, device="cuda")
+    ops.peer_gather_rows(ptr_t, rpo, ids, w, got)
+    assert torch.equal(got, table[ids])
+    got1 = torch.zeros(77, dtype=dtype, device="cuda")
+    ops.peer_gather_rows(ptr_b, rpo, ids, 1, got1)
+    assert torch.equal(got1, bt[ids])
+
+
+@pytest.mark.parametrize("coef_mode", [False, True])
+def test_group_build_owned_range_restricts_the_reduce(coef_mode):
+    """chk_group_build(own = [lo, hi)) + chk_reduce_apply update exactly the rows of the range a full reduce would, with the
+    same bits, and touch nothing outside it (owner-sharded tables: each rank reduces only the rows it owns)."""
+    from complexhyperbolickge_b200 import ops
+    g = torch.Generator().manual_seed(17)
+    N, r, B, nt = 400, 33, 16, 60
+    w, P = 2 * r, B * nt
+    S = B + P
+    ids = torch.randint(0, N, (S,), generator=g).cuda()
+    ids[B + 5:B + 5 + 80] = 123                                  # a long segment inside the owned range
+    table = (torch.randn(N, w, generator=g, dtype=torch.float64) * (0.5 / np.sqrt(w))).float().cuda()
+    state0 = torch.rand(N, w, generator=g).cuda()
+    g_ent = torch.randn(B, w, generator=g).cuda()
+    q = (torch.randn(B, w, generator=g) * (0.6 / np.sqrt(w))).cuda()
+    rows = torch.randn(P, w, generator=g).cuda()
+    cf = torch.randn(P, 4, generator=g).cuda()
+    hyper = torch.tensor([0.1, 1e-10, 0, 0, 0, 0, 0, 0], dtype=torch.float64, device="cuda")
+    res = []
+    for own in (None, (100, 250)):
+        param, st = table.clone(), state0.clone()
+        work = ops.group_workspace(N, S, "cuda")
+        col = dict(param=param, state0=st, dense=None)
+        if coef_mode:
+            col.update(src=[(g_ent, 0, B, 0), (q, B, S, 0)], pair=(cf, nt, 0))
+        else:
+            col.update(src=[(g_ent, 0, B, 0), (rows, B, S, 0)])
+        groups = [dict(ids=ids, n_keys=N, slots_per_rank=S, world=1, work=work, cols=[col])]
+        ops.group_build(ids, N, work, own=own)
+        ops.reduce_apply(param, ops.CHK_OPT_ADAGRAD, groups, hyper)
+        ops.step_finish(param, [work], None, None, None)
+        assert work[:4].abs().sum().item() == 0 and work[4:4 + N].abs().sum().item() == 0
+        res.append((param, st))
+    (pf, sf), (po, so) = res
+    assert torch.equal(po[100:250], pf[100:250]) and torch.equal(so[100:250], sf[100:250])
+    assert torch.equal(po[:100], table[:100]) and torch.equal(po[250:], table[250:]) and torch.equal(so[:100], state0[:100])
+    assert not torch.equal(pf[:100], table[:100])
