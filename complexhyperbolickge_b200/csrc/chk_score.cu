@@ -92,14 +92,17 @@ __device__ __forceinline__ void group_sum3(T& a, T& b, T& c) {
 // MODE 0: scores; MODE 1: adjoint from given d/dscores; MODE 2: training pass — scores, the negative-sampling loss terms
 // -logsigmoid(+s) (column 0) / -logsigmoid(-s) (columns >= 1) of KGOptimizer.neg_sampling_loss (reference
 // optimizers/kg_optimizer.py:115-122), their derivative and the adjoint, with every tail row gathered ONCE.
-template <typename T, int LOGL, int P, int MODE>
+// RC: the rank as a compile-time constant (0 = runtime A.r).  The training pass is instantiated for the BASELINE ranks 33 and 257:
+// ncu r2 showed a third of its warp instructions were integer address / predicate work (IADD3, IMAD, LEA, ISETP) that
+// constant row offsets and `k < r` tests fold away.
+template <typename T, int LOGL, int P, int MODE, int RC = 0>
 __global__ void __launch_bounds__(kWarps * 32, (sizeof(T) == 4 && P <= 5) ? 4 : 1) score_gather_kernel(SArgs<T> A) {   // fp32, rank <= 129: 64 registers, so a
     // 500-row batch (4 CTAs x 148 SMs = 592 slots) is ONE wave instead of 1.13 (ncu r2: 80 registers, 3 CTAs per SM, a second wave of 56 CTAs)
     constexpr bool BWD = MODE >= 1, TRAIN = MODE >= 2;          // MODE 3: the training pass on owner-sharded (peer) tables
     constexpr int L = 1 << LOGL, G = 32 / L;          // lanes per pair, pairs per warp
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gl = lane & (L - 1), grp = lane >> LOGL;
-    const int r = A.r;
+    const int r = RC > 0 ? RC : A.r;
     extern __shared__ unsigned char smem_raw[];
     T* red = reinterpret_cast<T*>(smem_raw);          // [kWarps][2r] for the grad_q reduction (BWD)
     __shared__ T red2[2][kWarps];                     // TRAIN: per-warp loss / bh-gradient partials
@@ -371,7 +374,8 @@ int launch_gather(const SArgs<T>& A, cudaStream_t st) {
         smem += (size_t)kWarps * kRingDepth * ring_slot_floats(A.r) * sizeof(float);
         static bool attr_set = false;
         if (!attr_set) {
-            if (cudaFuncSetAttribute((const void*)score_gather_kernel<T, 5, 9, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess) {
+            if (cudaFuncSetAttribute((const void*)score_gather_kernel<T, 5, 9, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess ||
+                cudaFuncSetAttribute((const void*)score_gather_kernel<T, 5, 9, MODE, 257>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess) {
                 chk_set_error("score_gather_kernel: cannot raise the dynamic shared memory limit"); return CHK_ECUDA;
             }
             attr_set = true;
@@ -380,7 +384,9 @@ int launch_gather(const SArgs<T>& A, cudaStream_t st) {
 #define CHK_LAUNCH(LOGL, P)                                                                         \
     score_gather_kernel<T, LOGL, P, MODE><<<(unsigned)blocks, kWarps * 32, smem, st>>>(A)
     const int r = A.r;
-    if (r <= 10) CHK_LAUNCH(1, 5);            // rank 9:   2 lanes x 5
+    if (MODE >= 2 && r == 33) score_gather_kernel<T, 3, 5, MODE, 33><<<(unsigned)blocks, kWarps * 32, smem, st>>>(A);
+    else if (MODE >= 2 && r == 257) score_gather_kernel<T, 5, 9, MODE, 257><<<(unsigned)blocks, kWarps * 32, smem, st>>>(A);
+    else if (r <= 10) CHK_LAUNCH(1, 5);       // rank 9:   2 lanes x 5
     else if (r <= 20) CHK_LAUNCH(2, 5);       // rank 17:  4 lanes x 5
     else if (r <= 40) CHK_LAUNCH(3, 5);       // rank 33:  8 lanes x 5 (4 pairs per warp)
     else if (r <= 80) CHK_LAUNCH(4, 5);       // rank 65: 16 lanes x 5

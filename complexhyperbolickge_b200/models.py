@@ -221,6 +221,9 @@ class FFTUnitBall(KGModel):
         filter lists are NOT mutated.  With ``self.process_group`` set, every rank counts over its
         contiguous slice of the entity table and the int64 counts are summed with one all_reduce."""
         from .ranking import rank_queries
+        if getattr(self, "_replicas_stale", False):
+            raise RuntimeError("the entity / bias tables are owner-sharded by FusedDataParallelKGOptimizer and this rank's copy is not "
+                               "current: call optimizer.sync_replicas() (epoch() does) before evaluating or saving the model")
         if isinstance(queries, np.ndarray):
             queries = torch.from_numpy(queries)
         return rank_queries(self, queries, self._filter_index(filters), batch_size)

@@ -239,7 +239,13 @@ class FusedDataParallelKGOptimizer(FusedKGOptimizer):
         for name, _ in self._sparse_params():
             for t in (self._symm[name][0], self._state_pad[name]):
                 dist.all_gather_into_tensor(t.view(-1), t[r * rpo:(r + 1) * rpo].reshape(-1), group=self.pg)
+        self.model._replicas_stale = False
         self.model.parameters_changed()
+
+    def _post_step(self):
+        super()._post_step()
+        if self.owner_sharded:
+            self.model._replicas_stale = True           # get_ranking refuses to run on a copy that is not current
 
     # ------------------------------------------------------------------------------------------ plan
     def _build_groups(self, pl):

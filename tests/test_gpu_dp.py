@@ -85,6 +85,15 @@ def _worker(rank, world, port, backend, mode, opt_name, q):
         m.release_eval_cache()
         single = m.get_ranking(ex[:64], filters, batch_size=20)
         assert torch.equal(sharded, single)
+        if opt.owner_sharded:                             # a bare step() leaves this rank's copy stale: evaluation must refuse
+            opt.step(ex[:Bg])
+            try:
+                m.get_ranking(ex[:8], filters, batch_size=8)
+                raise AssertionError("get_ranking ran on stale owner-sharded replicas")
+            except RuntimeError as e:
+                assert "sync_replicas" in str(e)
+            opt.sync_replicas()
+            m.get_ranking(ex[:8], filters, batch_size=8)
         if rank == 0:
             q.put((losses, params))
         # the captured CUDA graph holds NCCL work: release it before the communicator is torn down (destroy_process_group
