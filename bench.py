@@ -506,7 +506,9 @@ def measure_train(model, graph, opt_name, lr, B, neg, double_neg, steps, warmup,
                        "coefficients per negative instead of its gradient row), one-kernel ordered reduce that rebuilds the rows + Adagrad in place"
                        + ("; tables owner-sharded in symmetric memory: K3 reads tail rows from their owner over NVLink, each rank updates only its own rows"
                           if getattr(opt, "owner_sharded", False) else "; every replica applies every update")
-                       if getattr(opt, "sparse_entity", False) else "local segment-reduce into a flat dense gradient + ONE all_reduce + dense apply")
+                       if getattr(opt, "sparse_entity", False) else "local segment-reduce into a flat dense gradient")
+                    + ("; dense tables: gradient reduce-scatter + optimizer + parameter broadcast as ONE kernel over NVLink peer memory (chk_dp_fused_apply, no NCCL call)"
+                       if getattr(opt, "peer_dense", False) else "; dense tables: ONE NCCL all_reduce + dense apply on every replica")
                     if world > 1 else
                     "FusedKGOptimizer.fused_step: prep(sampler) -> K1 -> K3 fwd+loss+bwd (pair coefficients) -> K1 adjoint -> ordered segment-reduce "
                     "rebuilding the tail-row gradients + optimizer (CUDA graph)")}

@@ -588,6 +588,15 @@ def dense_apply(opt, tables, hyper, step_id):
     _launched(1)
 
 
+def dp_fused_apply(dtype_of, opt, world, rank, peer_grad, peer_param, peer_s0, peer_s1, peer_sig, n, hyper, step_id, local_state):
+    """Dense data-parallel step over peer memory: reduce-scatter of the flat gradients + optimizer + broadcast of the new
+    values, then wait + clear (chk_dp_fused_apply).  peer_*: int64 device tensors of `world` base pointers."""
+    _chk(peer_grad, peer_param, peer_s0, peer_s1, peer_sig, hyper, step_id, local_state)
+    _lib.check(_lib.lib().chk_dp_fused_apply(_dt(dtype_of), opt, world, rank, _p(peer_grad), _p(peer_param), _p(peer_s0), _p(peer_s1),
+                                             _p(peer_sig), n, _p(hyper), _p(step_id), _p(local_state), _stream()), "chk_dp_fused_apply")
+    _launched(2)
+
+
 def rowsum_groups(src, B, nj, width, out):
     _chk(src, out)
     _lib.check(_lib.lib().chk_rowsum_groups(_dt(src), _p(src), B, nj, width, _p(out), _stream()), "chk_rowsum_groups")

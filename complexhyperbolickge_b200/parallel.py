@@ -157,11 +157,13 @@ class FusedDataParallelKGOptimizer(FusedKGOptimizer):
       relation tables always): the local contributions are segment-reduced into dense gradients that are views of one flat
       buffer, ONE all_reduce sums it, chk_dense_apply runs torch.optim.Adagrad / Adam over the tables and clears it."""
 
-    def __init__(self, *args, process_group=None, sparse_exchange=None, owner_sharded=None, **kw):
+    def __init__(self, *args, process_group=None, sparse_exchange=None, owner_sharded=None, peer_dense=None, **kw):
         """sparse_exchange: None = decide by size (below); True / False force the entity-keyed tables onto the sparse row
         exchange / the dense all_reduce (tests and small-scale checks of the big-table path).  owner_sharded: None = shard the
         update of the sparse tables by owner whenever that path exists (NCCL, world > 1, pair coefficients, no N3 / F2);
-        False = every replica applies every update."""
+        False = every replica applies every update.  peer_dense: None = under NCCL the dense tables' gradient all_reduce, the
+        optimizer and the parameter broadcast run as ONE kernel over NVLink peer memory (chk_dp_fused_apply); False = NCCL
+        all_reduce + chk_dense_apply on every replica."""
         super().__init__(*args, **kw)
         self.pg = process_group
         self.world = _world(process_group)
@@ -189,12 +191,82 @@ class FusedDataParallelKGOptimizer(FusedKGOptimizer):
         self._flat_grad = flat
         self.owner_sharded = False
         self.own = None
+        self.peer_dense = False
+        nccl = self.world > 1 and dist.get_backend(self.pg) == "nccl"
+        if nccl and peer_dense is not False and self.world <= 8 and flat.numel() > 0:
+            self._setup_peer_dense()
+        elif peer_dense:
+            raise ValueError("peer_dense=True needs NCCL and 2..8 ranks")
         can = (self.sparse_entity and self.world > 1 and self._reg is None and self._pair_coef_mode()
                and dist.get_backend(self.pg) == "nccl")
         if owner_sharded and not can:
             raise ValueError("owner_sharded=True needs NCCL, world > 1, the sparse exchange, pair coefficients and no N3 / F2 regulariser")
         if can and owner_sharded is not False:
             self._setup_owner_shards()
+
+    # ------------------------------------------------------------------------------------------ dense tables over peer memory
+    def _setup_peer_dense(self):
+        """Flat gradient / parameter / optimizer-state buffers of the dense tables in symmetric memory (same layout on every
+        rank), a symmetric signal array, and the device arrays of peer base pointers chk_dp_fused_apply takes."""
+        import torch.distributed._symmetric_memory as symm_mem
+        group = self.pg if self.pg is not None else dist.group.WORLD
+        q = 4 * self.world
+        n = (self._flat_grad.numel() + q - 1) // q * q          # whole 4-element vectors per rank slice (the tail is padding)
+        dev, dt = self._flat_grad.device, self._flat_grad.dtype
+        keys = ("sum", None) if self.kind == "adagrad" else ("exp_avg", "exp_avg_sq")
+        self._peer = {}
+
+        def symm(numel, dtype):
+            t = symm_mem.empty((numel,), dtype=dtype, device=dev)
+            hdl = symm_mem.rendezvous(t, group)
+            t.zero_()
+            return t, hdl, torch.tensor(list(hdl.buffer_ptrs), dtype=torch.int64, device=dev)
+        bufs = {"grad": symm(n, dt), "param": symm(n, dt), "s0": symm(n, dt)}
+        if keys[1] is not None:
+            bufs["s1"] = symm(n, dt)
+        bufs["sig"] = symm(2 * self.world, torch.int32)
+        o = 0
+        for p in self._dense:                         # rebind gradients, parameters and optimizer state to views of the flat buffers
+            k = p.numel()
+            st = self.optimizer.state[p]
+            bufs["param"][0][o:o + k].view_as(p).copy_(p.data)
+            p.data = bufs["param"][0][o:o + k].view_as(p)
+            p.grad = bufs["grad"][0][o:o + k].view_as(p)
+            bufs["s0"][0][o:o + k].view_as(p).copy_(st[keys[0]])
+            st[keys[0]] = bufs["s0"][0][o:o + k].view_as(p)
+            if keys[1] is not None:
+                bufs["s1"][0][o:o + k].view_as(p).copy_(st[keys[1]])
+                st[keys[1]] = bufs["s1"][0][o:o + k].view_as(p)
+            o += k
+        self._flat_grad = bufs["grad"][0]
+        self._peer = bufs
+        self._peer_local = torch.zeros(4, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize()
+        dist.barrier(group=self.pg)
+        self.peer_dense = True
+        self.model.parameters_changed()
+
+    def check_peer_status(self):
+        """Raises if a peer did not arrive at a chk_dp_fused_apply step within its timeout (host sync; tests and epoch ends)."""
+        if self.peer_dense and int(self._peer_local[2].item()) != 0:
+            raise RuntimeError("chk_dp_fused_apply: a rank did not arrive (timeout); the replicas are out of step")
+
+    def _dense_step(self):
+        """Sum of the dense gradients over the ranks + optimizer + identical new values on every replica."""
+        m, st = self.model, self.optimizer.state
+        if self.peer_dense:
+            b = self._peer
+            ops.dp_fused_apply(m.entity.weight, ops.CHK_OPT_ADAM if self.kind == "adam" else ops.CHK_OPT_ADAGRAD, self.world, self.rank_id,
+                               b["grad"][2], b["param"][2], b["s0"][2], b["s1"][2] if "s1" in b else None, b["sig"][2],
+                               self._flat_grad.numel(), self._hyper, self._step_id, self._peer_local)
+            return
+        if self.world > 1:
+            dist.all_reduce(self._flat_grad, op=dist.ReduceOp.SUM, group=self.pg)
+        if self.kind == "adam":
+            tabs = [(p.data, p.grad, st[p]["exp_avg"], st[p]["exp_avg_sq"]) for p in self._dense]
+        else:
+            tabs = [(p.data, p.grad, st[p]["sum"], None) for p in self._dense]
+        ops.dense_apply(ops.CHK_OPT_ADAM if self.kind == "adam" else ops.CHK_OPT_ADAGRAD, tabs, self._hyper, self._step_id)
 
     # ------------------------------------------------------------------------------------------ owner-sharded tables
     def _sparse_params(self):
@@ -336,24 +408,18 @@ class FusedDataParallelKGOptimizer(FusedKGOptimizer):
         cur = torch.cuda.current_stream()
         cur.wait_stream(self._side)
         if self.sparse_entity and W > 1:
-            # relation tables: local row sums into the dense gradients, then their all_reduce on the side stream WHILE the main
-            # stream sums the entity-keyed rows of all ranks in (rank, slot) order and applies Adagrad in place
+            # relation tables: local row sums into the dense gradients, then their cross-rank step on the side stream WHILE the
+            # main stream sums the entity-keyed rows of all ranks in (rank, slot) order and applies Adagrad in place
             ops.reduce_apply(m.entity.weight, ops.CHK_OPT_NONE, pl.red_rel, self._hyper)
             self._side.wait_stream(cur)
             with torch.cuda.stream(self._side):
-                dist.all_reduce(self._flat_grad, op=dist.ReduceOp.SUM, group=self.pg)
+                self._dense_step()
             ops.reduce_apply(m.entity.weight, ops.CHK_OPT_ADAGRAD, pl.red_ent, self._hyper)
             cur.wait_stream(self._side)
         else:
             # one launch: the local row sums written into the dense gradients (and, single rank, the sparse tables updated in place)
             ops.reduce_apply(m.entity.weight, ops.CHK_OPT_ADAGRAD if self.sparse_entity else ops.CHK_OPT_NONE, pl.red, self._hyper)
-            if W > 1:
-                dist.all_reduce(self._flat_grad, op=dist.ReduceOp.SUM, group=self.pg)
-        if self.kind == "adam":
-            tabs = [(p.data, p.grad, st[p]["exp_avg"], st[p]["exp_avg_sq"]) for p in self._dense]
-        else:
-            tabs = [(p.data, p.grad, st[p]["sum"], None) for p in self._dense]
-        ops.dense_apply(ops.CHK_OPT_ADAM if self.kind == "adam" else ops.CHK_OPT_ADAGRAD, tabs, self._hyper, self._step_id)
+            self._dense_step()
         ops.step_finish(m.entity.weight, pl.works, pl.loss_part, self._loss_sum, self._step_id)
 
     def step(self, global_batch):
@@ -388,4 +454,5 @@ class FusedDataParallelKGOptimizer(FusedKGOptimizer):
             dist.all_reduce(total, op=dist.ReduceOp.SUM, group=self.pg)
         self.sync_optimizer_state()
         self.sync_replicas()
+        self.check_peer_status()
         return total.item() / max(nb, 1)

@@ -233,6 +233,17 @@ int chk_step_finish(int dtype, void* const* group_works, int n_groups, const voi
  * whole tables from a dense gradient, which is cleared (run.py:205 hands the dense tables to torch.optim). */
 typedef struct chk_dense_tab { void* param; void* grad; void* state0; void* state1; int64_t n; } chk_dense_tab;
 int chk_dense_apply(int dtype, int opt, const chk_dense_tab* tabs, int n_tables, const double* hyper, const int32_t* step_id, void* stream);
+/* Data-parallel dense-gradient step over NVLink peer memory (no NCCL call; no reference counterpart): the flat gradient, parameter
+ * and optimizer-state buffers of every rank live in symmetric memory with the same layout (peer_* = device arrays of `world`
+ * base pointers, n elements each, n a multiple of 4 * world, 16-byte aligned).  Every rank sums its 1/world slice of the `world` gradient buffers in ascending rank order,
+ * applies torch.optim.Adagrad (state0 = sum) / Adam (state0, state1 = exp_avg, exp_avg_sq; *step_id = 1-based step) to it and
+ * stores the new parameter / state values into EVERY replica; a second kernel waits for all slices and clears the local
+ * gradient buffer.  peer_signal: int32[2 * world] per rank, zero-initialised; local_state: int32[4], zero-initialised
+ * ([2] becomes non-zero if a peer did not arrive within ~4 s).  Every rank must make the same sequence of calls. */
+int chk_dp_fused_apply(int dtype, int opt, int world, int rank, const void* const* peer_grad, void* const* peer_param,
+                       void* const* peer_state0, void* const* peer_state1, int32_t* const* peer_signal, int64_t n,
+                       const double* hyper, const int32_t* step_id, int32_t* local_state, void* stream);
+
 /* out[b,:] = sum_j in[b,j,:] in a fixed order — eight interleaved partial sums (j mod 8), added in ascending order — so the
  * result is bit-reproducible (double_neg: the nt per-pair relation-row gradients of a triple share a row). */
 int chk_rowsum_groups(int dtype, const void* in, int64_t B, int64_t nj, int64_t width, void* out, void* stream);
