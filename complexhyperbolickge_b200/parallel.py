@@ -376,8 +376,10 @@ class FusedDataParallelKGOptimizer(FusedKGOptimizer):
         cur = torch.cuda.current_stream()
         self._side.wait_stream(cur)
         with torch.cuda.stream(self._side):                 # owner-sharded: only the slots naming this rank's rows are grouped
-            ops.group_build(pl.ent_group_ids, self.model.sizes[0], pl.w_ent, own=self.own)
             ops.group_build(pl.rels_b, self.model.rel.weight.shape[0], pl.w_rel)
+            ops.group_build(pl.ent_group_ids, self.model.sizes[0], pl.w_ent, own=self.own)
+            self._ev_grouped = torch.cuda.Event()
+            self._ev_grouped.record(self._side)
 
     def _head_tables(self, pl, learn):
         if not self.owner_sharded:
@@ -398,25 +400,25 @@ class FusedDataParallelKGOptimizer(FusedKGOptimizer):
                                     pl.grad_q, pl.grow, pl.g_bh if learn else None, pair_coef=pl.coef)
 
     def _apply(self, pl):
-        m, st = self.model, self.optimizer.state
+        m = self.model
         W = self.world
-        if self.sparse_entity:
-            if W > 1:
-                dist.all_gather_into_tensor(pl.all_flat.view(-1), pl.flat, group=self.pg)
-            else:
-                pl.all_flat.view(-1).copy_(pl.flat)
         cur = torch.cuda.current_stream()
-        cur.wait_stream(self._side)
         if self.sparse_entity and W > 1:
-            # relation tables: local row sums into the dense gradients, then their cross-rank step on the side stream WHILE the
-            # main stream sums the entity-keyed rows of all ranks in (rank, slot) order and applies Adagrad in place
-            ops.reduce_apply(m.entity.weight, ops.CHK_OPT_NONE, pl.red_rel, self._hyper)
-            self._side.wait_stream(cur)
+            # side stream (behind the grouping): relation tables — local row sums into the dense gradients, then their cross-rank
+            # step — WHILE the main stream gathers every rank's contribution buffer, sums the entity-keyed rows of all ranks in
+            # (rank, slot) order and applies Adagrad in place
+            self._side.wait_stream(cur)                                     # the K1 adjoint's relation-row gradients
             with torch.cuda.stream(self._side):
+                ops.reduce_apply(m.entity.weight, ops.CHK_OPT_NONE, pl.red_rel, self._hyper)
                 self._dense_step()
+            dist.all_gather_into_tensor(pl.all_flat.view(-1), pl.flat, group=self.pg)
+            cur.wait_event(self._ev_grouped)                                # the union of the entity slots is grouped
             ops.reduce_apply(m.entity.weight, ops.CHK_OPT_ADAGRAD, pl.red_ent, self._hyper)
             cur.wait_stream(self._side)
         else:
+            if self.sparse_entity:
+                pl.all_flat.view(-1).copy_(pl.flat)
+            cur.wait_stream(self._side)
             # one launch: the local row sums written into the dense gradients (and, single rank, the sparse tables updated in place)
             ops.reduce_apply(m.entity.weight, ops.CHK_OPT_ADAGRAD if self.sparse_entity else ops.CHK_OPT_NONE, pl.red, self._hyper)
             self._dense_step()
