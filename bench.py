@@ -502,7 +502,9 @@ def measure_train(model, graph, opt_name, lr, B, neg, double_neg, steps, warmup,
            "algorithmic_bytes_per_triple": bpt,
            "hbm_frac_per_gpu": (Bg / world) / (ms * 1e-3) * bpt / 1e9 / hbm,
            "path": ("FusedDataParallelKGOptimizer.step: fused chain per rank on rows rank::world (CUDA graph incl. NCCL), "
-                    + ("sparse exchange: all_gather of slot ids + per-rank contributions (head-gradient rows, query rows, 16 B of pair "
+                    + ("sparse exchange: all_gather" + (" by peer reads of symmetric buffers behind a flag barrier (chk_dp_all_gather, no NCCL call)"
+                                                        if getattr(opt, "peer_exchange", False) else " (NCCL)")
+                       + " of slot ids + per-rank contributions (head-gradient rows, query rows, 16 B of pair "
                        "coefficients per negative instead of its gradient row), one-kernel ordered reduce that rebuilds the rows + Adagrad in place"
                        + ("; tables owner-sharded in symmetric memory: K3 reads tail rows from their owner over NVLink, each rank updates only its own rows"
                           if getattr(opt, "owner_sharded", False) else "; every replica applies every update")

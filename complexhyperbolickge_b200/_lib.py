@@ -89,6 +89,7 @@ SIGNATURES = {
     "chk_dense_apply": (_i, [_i, _i, ctypes.POINTER(DenseTab), _i, _p, _p, _p]),
     "chk_rowsum_groups": (_i, [_i, _p, _i64, _i64, _i64, _p, _p]),
     "chk_dp_fused_apply": (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p, _i64, _p, _p, _p, _p]),
+    "chk_dp_all_gather": (_i, [_i, _i, _p, _i64, _p, _p, _i, _p, _p]),
     "chk_reg_factors": (_i, [_i, _i, ctypes.c_double, _p, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _p, _i64, _p, _i64, _p, _i64,
                              _p, _i64, _p, _p]),
     "chk_row_hnorm": (_i, [_i, _i, _i64, _p, _p, _p]),

@@ -33,7 +33,7 @@ struct DpArgs {
     int* const* sig;                                                                  // peer signal arrays, int[2 * world] each
     int world, rank; int64_t n;
     const double* hyper; const int* step_id;
-    int* local;                                                                       // [0] epoch  [1] ticket A  [2] status  [3] ticket C
+    int* local;                                                                       // [0] epoch  [1] ticket A  [2] status  [3] ticket C  ([4..7]: chk_dp_all_gather)
 };
 
 // threads t < world of the block poll slot `base + t` of this rank's signal array until it reaches v
@@ -167,7 +167,55 @@ __global__ void __launch_bounds__(256) dp_wait_clear_kernel(DpArgs A) {
     if (threadIdx.x == 0 && atomicAdd(A.local + 3, 1) == (int)gridDim.x - 1) { A.local[3] = 0; A.local[0] = E + 1; }
 }
 
+// all_gather by peer reads: after a flag barrier ("my block is complete") every rank copies the `world` blocks from their owners'
+// symmetric buffers into its local [world, bytes] buffer.  The barrier also orders everything before it on every rank against
+// everything after it on every other rank (the owner-sharded tables rely on that, parallel.py).
+struct AgArgs {
+    const void* const* src; void* dst; int64_t bytes; int* const* sig; int slot; int world, rank; int* local; int epoch_idx, ticket_idx;
+};
+template <typename V>
+__global__ void __launch_bounds__(256) dp_all_gather_kernel(AgArgs A) {
+    const int E = *reinterpret_cast<volatile int*>(A.local + A.epoch_idx);
+    const int v = E + 1;
+    if (blockIdx.x == 0 && (int)threadIdx.x < A.world) st_release_sys(A.sig[threadIdx.x] + A.slot + A.rank, v);
+    if ((int)threadIdx.x < A.world) {
+        const int* s = A.sig[A.rank] + A.slot + threadIdx.x;
+        const long long t0 = clock64();
+        while (ld_acquire_sys(s) < v) {
+            if (clock64() - t0 > 8000000000LL) { A.local[2] = 1; break; }
+        }
+    }
+    __syncthreads();
+    const int64_t nv = A.bytes / (int64_t)sizeof(V), total = nv * A.world;
+    V* dst = reinterpret_cast<V*>(A.dst);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int k = (int)(i / nv);
+        dst[i] = __ldcg(reinterpret_cast<const V*>(A.src[k]) + (i - (int64_t)k * nv));
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(A.local + A.ticket_idx, 1) == (int)gridDim.x - 1) { A.local[A.ticket_idx] = 0; A.local[A.epoch_idx] = v; }
+}
+
 }  // namespace
+
+extern "C" int chk_dp_all_gather(int world, int rank, const void* const* peer_src, int64_t bytes_per_rank, void* dst,
+                                 int32_t* const* peer_signal, int channel, int32_t* local_state, void* stream) {
+    if (bytes_per_rank == 0) return CHK_OK;
+    if (world < 2 || world > DP_MAX_WORLD || rank < 0 || rank >= world || bytes_per_rank < 0 || (bytes_per_rank & 7) || !peer_src || !dst ||
+        !peer_signal || !local_state || channel < 0 || channel > 1) {
+        chk_set_error("chk_dp_all_gather: bad argument (bytes_per_rank must be a multiple of 8, channel 0 or 1)"); return CHK_EINVAL;
+    }
+    AgArgs A{peer_src, dst, bytes_per_rank, (int* const*)peer_signal, (2 + channel) * world, world, rank, (int*)local_state, 4 + 2 * channel, 5 + 2 * channel};
+    const bool v16 = (bytes_per_rank & 15) == 0 && (((uintptr_t)dst) & 15) == 0;
+    const int64_t nvec = bytes_per_rank / (v16 ? 16 : 8) * world;
+    // at most two 256-thread blocks per SM: the blocks spin until every peer has arrived and must never fill an SM (a rank's
+    // other peer-memory kernel may have to start beside them for the peers to get its flag)
+    int grid = (int)((nvec + 255) / 256); if (grid > 148 * 2) grid = 148 * 2; if (grid < 1) grid = 1;
+    if (v16) dp_all_gather_kernel<uint4><<<grid, 256, 0, (cudaStream_t)stream>>>(A);
+    else dp_all_gather_kernel<uint2><<<grid, 256, 0, (cudaStream_t)stream>>>(A);
+    CHK_CUDA_LAUNCH_CHECK("dp_all_gather_kernel");
+    return CHK_OK;
+}
 
 extern "C" int chk_dp_fused_apply(int dtype, int opt, int world, int rank, const void* const* peer_grad, void* const* peer_param,
                                   void* const* peer_state0, void* const* peer_state1, int32_t* const* peer_signal, int64_t n,

@@ -597,6 +597,14 @@ def dp_fused_apply(dtype_of, opt, world, rank, peer_grad, peer_param, peer_s0, p
     _launched(2)
 
 
+def dp_all_gather(world, rank, peer_src, bytes_per_rank, dst, peer_sig, channel, local_state):
+    """all_gather by peer reads behind a flag barrier (chk_dp_all_gather)."""
+    _chk(peer_src, dst, peer_sig, local_state)
+    _lib.check(_lib.lib().chk_dp_all_gather(world, rank, _p(peer_src), bytes_per_rank, _p(dst), _p(peer_sig), channel, _p(local_state),
+                                            _stream()), "chk_dp_all_gather")
+    _launched(1)
+
+
 def rowsum_groups(src, B, nj, width, out):
     _chk(src, out)
     _lib.check(_lib.lib().chk_rowsum_groups(_dt(src), _p(src), B, nj, width, _p(out), _stream()), "chk_rowsum_groups")

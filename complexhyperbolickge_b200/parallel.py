@@ -157,13 +157,15 @@ class FusedDataParallelKGOptimizer(FusedKGOptimizer):
       relation tables always): the local contributions are segment-reduced into dense gradients that are views of one flat
       buffer, ONE all_reduce sums it, chk_dense_apply runs torch.optim.Adagrad / Adam over the tables and clears it."""
 
-    def __init__(self, *args, process_group=None, sparse_exchange=None, owner_sharded=None, peer_dense=None, **kw):
+    def __init__(self, *args, process_group=None, sparse_exchange=None, owner_sharded=None, peer_dense=None, peer_exchange=None, **kw):
         """sparse_exchange: None = decide by size (below); True / False force the entity-keyed tables onto the sparse row
         exchange / the dense all_reduce (tests and small-scale checks of the big-table path).  owner_sharded: None = shard the
         update of the sparse tables by owner whenever that path exists (NCCL, world > 1, pair coefficients, no N3 / F2);
         False = every replica applies every update.  peer_dense: None = under NCCL the dense tables' gradient all_reduce, the
         optimizer and the parameter broadcast run as ONE kernel over NVLink peer memory (chk_dp_fused_apply); False = NCCL
-        all_reduce + chk_dense_apply on every replica."""
+        all_reduce + chk_dense_apply on every replica.  peer_exchange: None = under NCCL the two all_gathers of the sparse exchange
+        (slot ids, contribution buffers) are peer reads of symmetric buffers behind a flag barrier (chk_dp_all_gather);
+        False = NCCL all_gather."""
         super().__init__(*args, **kw)
         self.pg = process_group
         self.world = _world(process_group)
@@ -192,7 +194,13 @@ class FusedDataParallelKGOptimizer(FusedKGOptimizer):
         self.owner_sharded = False
         self.own = None
         self.peer_dense = False
+        self.peer_exchange = False
         nccl = self.world > 1 and dist.get_backend(self.pg) == "nccl"
+        if nccl and self.world <= 8 and (peer_dense is not False or peer_exchange is not False):
+            self._setup_peer_signals()
+            self.peer_exchange = peer_exchange is not False and self.sparse_entity
+        elif peer_exchange:
+            raise ValueError("peer_exchange=True needs NCCL and 2..8 ranks")
         if nccl and peer_dense is not False and self.world <= 8 and flat.numel() > 0:
             self._setup_peer_dense()
         elif peer_dense:
@@ -204,27 +212,50 @@ class FusedDataParallelKGOptimizer(FusedKGOptimizer):
         if can and owner_sharded is not False:
             self._setup_owner_shards()
 
-    # ------------------------------------------------------------------------------------------ dense tables over peer memory
+    # ------------------------------------------------------------------------------------------ peer memory
+    def _symm_alloc(self, numel, dtype):
+        """(zeroed symmetric buffer, handle, device tensor of the `world` peer base pointers); collective."""
+        import torch.distributed._symmetric_memory as symm_mem
+        group = self.pg if self.pg is not None else dist.group.WORLD
+        dev = self.model.entity.weight.device
+        t = symm_mem.empty((numel,), dtype=dtype, device=dev)
+        hdl = symm_mem.rendezvous(t, group)
+        t.zero_()
+        return t, hdl, torch.tensor(list(hdl.buffer_ptrs), dtype=torch.int64, device=dev)
+
+    def _setup_peer_signals(self):
+        """Flag arrays of the peer-memory kernels (chk_dp_fused_apply, chk_dp_all_gather): symmetric int32[4 * world] + local state."""
+        self._peer_sig = self._symm_alloc(4 * self.world, torch.int32)
+        self._peer_local = torch.zeros(8, dtype=torch.int32, device=self.model.entity.weight.device)
+        torch.cuda.synchronize()
+        dist.barrier(group=self.pg)
+
+    def _exchange_buffer(self, pl, name, numel, dtype, device):
+        if not self.peer_exchange:
+            return super()._exchange_buffer(pl, name, numel, dtype, device)
+        t, hdl, ptrs = self._symm_alloc(numel, dtype)          # collective: every rank builds the same plans in the same order
+        setattr(pl, "_x_" + name, (t, hdl, ptrs))
+        return t
+
+    def _all_gather(self, pl, name, dst, src, channel):
+        """dst[k] = rank k's `src`; also the ordering point of the step (see the class docstring)."""
+        if self.peer_exchange:
+            ops.dp_all_gather(self.world, self.rank_id, getattr(pl, "_x_" + name)[2], src.numel() * src.element_size(), dst,
+                              self._peer_sig[2], channel, self._peer_local)
+        else:
+            dist.all_gather_into_tensor(dst.view(-1), src, group=self.pg)
+
     def _setup_peer_dense(self):
         """Flat gradient / parameter / optimizer-state buffers of the dense tables in symmetric memory (same layout on every
         rank), a symmetric signal array, and the device arrays of peer base pointers chk_dp_fused_apply takes."""
-        import torch.distributed._symmetric_memory as symm_mem
-        group = self.pg if self.pg is not None else dist.group.WORLD
         q = 4 * self.world
         n = (self._flat_grad.numel() + q - 1) // q * q          # whole 4-element vectors per rank slice (the tail is padding)
         dev, dt = self._flat_grad.device, self._flat_grad.dtype
         keys = ("sum", None) if self.kind == "adagrad" else ("exp_avg", "exp_avg_sq")
-        self._peer = {}
-
-        def symm(numel, dtype):
-            t = symm_mem.empty((numel,), dtype=dtype, device=dev)
-            hdl = symm_mem.rendezvous(t, group)
-            t.zero_()
-            return t, hdl, torch.tensor(list(hdl.buffer_ptrs), dtype=torch.int64, device=dev)
-        bufs = {"grad": symm(n, dt), "param": symm(n, dt), "s0": symm(n, dt)}
+        bufs = {"grad": self._symm_alloc(n, dt), "param": self._symm_alloc(n, dt), "s0": self._symm_alloc(n, dt)}
         if keys[1] is not None:
-            bufs["s1"] = symm(n, dt)
-        bufs["sig"] = symm(2 * self.world, torch.int32)
+            bufs["s1"] = self._symm_alloc(n, dt)
+        bufs["sig"] = self._peer_sig
         o = 0
         for p in self._dense:                         # rebind gradients, parameters and optimizer state to views of the flat buffers
             k = p.numel()
@@ -240,7 +271,6 @@ class FusedDataParallelKGOptimizer(FusedKGOptimizer):
             o += k
         self._flat_grad = bufs["grad"][0]
         self._peer = bufs
-        self._peer_local = torch.zeros(4, dtype=torch.int32, device=dev)
         torch.cuda.synchronize()
         dist.barrier(group=self.pg)
         self.peer_dense = True
@@ -248,8 +278,8 @@ class FusedDataParallelKGOptimizer(FusedKGOptimizer):
 
     def check_peer_status(self):
         """Raises if a peer did not arrive at a chk_dp_fused_apply step within its timeout (host sync; tests and epoch ends)."""
-        if self.peer_dense and int(self._peer_local[2].item()) != 0:
-            raise RuntimeError("chk_dp_fused_apply: a rank did not arrive (timeout); the replicas are out of step")
+        if (self.peer_dense or self.peer_exchange) and int(self._peer_local[2].item()) != 0:
+            raise RuntimeError("a rank did not arrive at a peer-memory step (timeout); the replicas are out of step")
 
     def _dense_step(self):
         """Sum of the dense gradients over the ranks + optimizer + identical new values on every replica."""
@@ -370,7 +400,7 @@ class FusedDataParallelKGOptimizer(FusedKGOptimizer):
     # ------------------------------------------------------------------------------------------ step
     def _after_prep(self, pl):
         if self.sparse_entity and self.world > 1:           # everyone's slot ids, so the union can be grouped during the local pass
-            dist.all_gather_into_tensor(pl.all_ids.view(-1), pl.ent_ids, group=self.pg)
+            self._all_gather(pl, "ids", pl.all_ids, pl.ent_ids, 0)
         elif self.sparse_entity:
             pl.all_ids.view(-1).copy_(pl.ent_ids)
         cur = torch.cuda.current_stream()
@@ -411,7 +441,7 @@ class FusedDataParallelKGOptimizer(FusedKGOptimizer):
             with torch.cuda.stream(self._side):
                 ops.reduce_apply(m.entity.weight, ops.CHK_OPT_NONE, pl.red_rel, self._hyper)
                 self._dense_step()
-            dist.all_gather_into_tensor(pl.all_flat.view(-1), pl.flat, group=self.pg)
+            self._all_gather(pl, "flat", pl.all_flat, pl.flat, 1)
             cur.wait_event(self._ev_grouped)                                # the union of the entity slots is grouped
             ops.reduce_apply(m.entity.weight, ops.CHK_OPT_ADAGRAD, pl.red_ent, self._hyper)
             cur.wait_stream(self._side)

@@ -51,7 +51,7 @@ class _Plan:
         self.P = P = B * nt                               # (query, tail) pairs
         i64 = dict(dtype=torch.int64, device=dev)
         self.batch = torch.zeros((B, 3), **i64)
-        self.ent_ids = torch.zeros((Bq + P,), **i64)      # slot -> entity id: [heads | tails], the entity group's key array
+        self.ent_ids = o._exchange_buffer(self, "ids", Bq + P, torch.int64, dev)      # slot -> entity id: [heads | tails], the entity group's key array
         self.heads, self.tails = self.ent_ids[:Bq], self.ent_ids[Bq:]
         self.rels = torch.zeros((Bq,), **i64)
         self.rels_b = self.rels if not self.dn else torch.zeros((B,), **i64)
@@ -71,7 +71,7 @@ class _Plan:
             o_gs = o_row + _round4(P * 2 * r)
         o_bh = o_gs + _round4(P)
         flat_len = o_bh + (0 if self.dn else _round4(B))
-        self.flat = torch.zeros((flat_len,), dtype=dt, device=dev)
+        self.flat = o._exchange_buffer(self, "flat", flat_len, dt, dev)
         self.g_ent = self.flat[o_ent:o_ent + Bq * 2 * r].view(Bq, 2 * r)
         if self.coef_mode:
             self.q = self.flat[o_row:o_row + Bq * 2 * r].view(Bq, 2 * r)
@@ -176,6 +176,10 @@ class FusedKGOptimizer(KGOptimizer):
         if pl.coef_mode:
             return ([head_src, (view("q", pl.q), Bq, S_e, rank_stride)], (view("coef", pl.coef), 0 if pl.dn else pl.nt, rank_stride))
         return [head_src, (view("grow", pl.grow), Bq, S_e, rank_stride)], None
+
+    def _exchange_buffer(self, pl, name, numel, dtype, device):
+        """Buffers of a plan that travel in the data-parallel exchange (slot ids, contribution buffer); plain memory here."""
+        return torch.zeros((numel,), dtype=dtype, device=device)
 
     def _injected_sampler(self):
         return type(self).get_neg_samples is not KGOptimizer.get_neg_samples

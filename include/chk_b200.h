@@ -238,11 +238,18 @@ int chk_dense_apply(int dtype, int opt, const chk_dense_tab* tabs, int n_tables,
  * base pointers, n elements each, n a multiple of 4 * world, 16-byte aligned).  Every rank sums its 1/world slice of the `world` gradient buffers in ascending rank order,
  * applies torch.optim.Adagrad (state0 = sum) / Adam (state0, state1 = exp_avg, exp_avg_sq; *step_id = 1-based step) to it and
  * stores the new parameter / state values into EVERY replica; a second kernel waits for all slices and clears the local
- * gradient buffer.  peer_signal: int32[2 * world] per rank, zero-initialised; local_state: int32[4], zero-initialised
+ * gradient buffer.  peer_signal: int32[4 * world] per rank (symmetric), zero-initialised; local_state: int32[8], zero-initialised
  * ([2] becomes non-zero if a peer did not arrive within ~4 s).  Every rank must make the same sequence of calls. */
 int chk_dp_fused_apply(int dtype, int opt, int world, int rank, const void* const* peer_grad, void* const* peer_param,
                        void* const* peer_state0, void* const* peer_state1, int32_t* const* peer_signal, int64_t n,
                        const double* hyper, const int32_t* step_id, int32_t* local_state, void* stream);
+
+/* all_gather by peer reads (no NCCL call): a flag barrier ("my block is complete"; it also orders everything before the call on
+ * every rank against everything after it on every other rank), then dst[k] = the bytes_per_rank bytes at peer_src[k] for every
+ * k.  peer_src: device array of `world` base pointers of a symmetric buffer; bytes_per_rank a multiple of 8; channel 0 / 1 = two
+ * independent flag sets in the peer_signal / local_state arrays of chk_dp_fused_apply. */
+int chk_dp_all_gather(int world, int rank, const void* const* peer_src, int64_t bytes_per_rank, void* dst,
+                      int32_t* const* peer_signal, int channel, int32_t* local_state, void* stream);
 
 /* out[b,:] = sum_j in[b,j,:] in a fixed order — eight interleaved partial sums (j mod 8), added in ascending order — so the
  * result is bit-reproducible (double_neg: the nt per-pair relation-row gradients of a triple share a row). */

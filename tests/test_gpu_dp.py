@@ -124,7 +124,7 @@ def test_dp_epoch_equals_single_gpu_epoch(mode, opt_name):
     for p in procs:
         p.start()
     try:
-        got = q.get(timeout=300)
+        got = q.get(timeout=150)
         for p in procs:
             p.join(timeout=60)
             assert p.exitcode == 0, "a rank did not exit cleanly"
