@@ -195,3 +195,26 @@ def test_bench_cycles_examples_instead_of_slicing_past_the_end():
     out = bench.cycle_batches(ex, 7, 4)
     assert out.shape == (7, 4, 3)
     assert torch.equal(out.view(-1, 3)[:10], ex) and torch.equal(out.view(-1, 3)[10:20], ex)
+
+
+def test_header_is_c_and_struct_layouts_match_ctypes(tmp_path):
+    """include/chk_b200.h compiles as plain C (the boundary is a C ABI) and the structs it declares have the size / field
+    offsets of their ctypes mirrors in _lib.py (an ABI drift between the header and the binding would corrupt arguments)."""
+    import ctypes
+    import shutil
+    import subprocess
+    from complexhyperbolickge_b200 import _lib
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "abi.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "chk_b200.h"\n'
+                   'int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(chk_red_col), sizeof(chk_red_group), '
+                   'sizeof(chk_eval_args), sizeof(chk_dense_tab), sizeof(chk_table_desc), offsetof(chk_red_col, pair_coef), '
+                   'offsetof(chk_red_group, cols), offsetof(chk_eval_args, scratch)); return 0; }\n')
+    exe = tmp_path / "abi"
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", inc, str(src), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    want = [ctypes.sizeof(_lib.RedCol), ctypes.sizeof(_lib.RedGroup), ctypes.sizeof(_lib.EvalArgs), ctypes.sizeof(_lib.DenseTab),
+            ctypes.sizeof(_lib.TableDesc), _lib.RedCol.pair_coef.offset, _lib.RedGroup.cols.offset, _lib.EvalArgs.scratch.offset]
+    assert got == want
