@@ -479,7 +479,7 @@ def measure_train(model, graph, opt_name, lr, B, neg, double_neg, steps, warmup,
         if world > 1:
             opt.step(pinned[i])                                       # rows rank::world, H2D inside
         else:
-            opt.fused_step(pinned[i].to(device, non_blocking=True))
+            opt.fused_step(pinned[i])                                 # pinned host batch: ONE async H2D copy into the step's id buffer
     launches = ops.launch_count - launches0
     lv = opt._loss_sum.double()
     if world > 1:

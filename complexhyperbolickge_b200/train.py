@@ -319,8 +319,9 @@ class FusedKGOptimizer(KGOptimizer):
         self._apply(pl)
 
     def fused_step(self, batch, n_valid=None):
-        """One training step on a device batch (B, 3); the loss is added to the device-side epoch accumulator.  n_valid < B
-        marks the trailing rows as padding (zero loss, zero gradient)."""
+        """One training step on a batch (B, 3) — a device tensor or a pinned host tensor (one asynchronous copy into the step's
+        id buffer); the loss is added to the device-side epoch accumulator.  n_valid < B marks the trailing rows as padding
+        (zero loss, zero gradient)."""
         B = batch.shape[0]
         if B == 0:
             return
